@@ -1,0 +1,185 @@
+/* infimum_b200 — C ABI of the B200-native Poseidon-BN254 hasher and poll-tree
+ * merge, the drop-in boundary for the one data-parallel hot path of
+ * rhysbalevicius/infimum (citations are relative to the reference checkout).
+ *
+ * Every entry point below is what a `gpu` (std-only) feature of the pallet
+ * would bind over FFI in place of the reference function named beside it; the
+ * Rust shim a maintainer would add is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Field elements travel as 32-byte big-endian `HashBytes`
+ *     (pallet/src/poll/poll.rs:9).  Inputs may be any 256-bit value and are
+ *     reduced mod p exactly like `Fr::from_be_bytes_mod_order`
+ *     (pallet/src/poll/state.rs:290); outputs are canonical (< p).
+ *   - Arrays are dense row-major: n hashes of k inputs = n*k*32 bytes.
+ *   - The caller owns every buffer; the library keeps no pointer after return.
+ *   - Calls on one inf_ctx must be serialised by the caller (like `&mut self`,
+ *     pallet/src/hash/poseidon.rs:78); distinct contexts are independent.
+ *   - Host-buffer calls are synchronous.  `_dev` calls take device pointers,
+ *     enqueue on the given CUDA stream (a cudaStream_t passed as void*, NULL =
+ *     the context's own stream) and return without synchronising unless noted.
+ *   - There is no CPU fallback: without a usable CUDA device inf_init fails.
+ *
+ * Return codes (int): 0 ok.
+ *   1..4    MerkleTreeError as u8, pallet/src/poll/state.rs:106-118
+ *   16..31  PoseidonError / argument errors, pallet/src/hash/poseidon.rs:13-31
+ *   64..    CUDA failure (the Rust side maps these to HashFailed = 3)
+ */
+#ifndef INFIMUM_B200_H
+#define INFIMUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INF_OK 0
+/* MerkleTreeError -> u8 (state.rs:106-118) */
+#define INF_ERR_TREE_ALREADY_FULL 1
+#define INF_ERR_TREE_ALREADY_MERGED 2
+#define INF_ERR_HASH_FAILED 3
+#define INF_ERR_MERGE_FAILED 4
+/* PoseidonError (poseidon.rs:13-31) */
+#define INF_ERR_INVALID_NUMBER_OF_INPUTS 16
+#define INF_ERR_EMPTY_INPUT 17
+#define INF_ERR_INVALID_INPUT_LENGTH 18
+#define INF_ERR_INVALID_WIDTH_CIRCOM 19
+/* argument errors with no reference counterpart */
+#define INF_ERR_NULL_POINTER 24
+#define INF_ERR_BAD_ARITY 25
+#define INF_ERR_BAD_DEPTH 26
+/* device */
+#define INF_ERR_NO_DEVICE 64
+#define INF_ERR_CUDA 65
+#define INF_ERR_OUT_OF_MEMORY 66
+
+/* flags */
+#define INF_FLAG_LITTLE_ENDIAN 1u /* hash_bytes_le wire order (poseidon.rs:233-250) */
+
+typedef struct inf_ctx inf_ctx;
+
+/* ---- lifetime -------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` (ordinal).  Derives the Poseidon
+ * tables (what get_poseidon_parameters returns, parameters.rs:35, plus the
+ * optimised-schedule tables) and the Merkle zero tables (zeroes.rs:1-71) and
+ * uploads them. */
+int inf_init(int device, inf_ctx** out);
+void inf_destroy(inf_ctx* ctx);
+/* Static description of a return code. */
+const char* inf_strerror(int code);
+/* Text of the last CUDA error seen by this context ("" if none). */
+const char* inf_last_cuda_error(const inf_ctx* ctx);
+/* Library version / build info. */
+const char* inf_version(void);
+
+/* ---- Poseidon hasher --------------------------------------------------------
+ * Replaces Poseidon::<Fr>::new_circom(n_inputs) / with_domain_tag_circom
+ * (poseidon.rs:302-327) followed by PoseidonHasher::hash (poseidon.rs:162-208)
+ * or PoseidonBytesHasher::hash_bytes_be / _le (poseidon.rs:213-250), applied
+ * to `n` independent input tuples.
+ *   n_inputs     1..12 (width t = n_inputs+1 <= 13) else INVALID_WIDTH_CIRCOM
+ *   domain_tag   32 bytes in the same wire order as the inputs, or NULL for 0
+ *   in           n * n_inputs * 32 bytes
+ *   out          n * 32 bytes
+ */
+int inf_poseidon_hash_batch(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                            const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
+                            uint8_t* out);
+int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                                const uint8_t* domain_tag /* host */, const void* d_in, uint64_t n,
+                                void* d_out, void* stream);
+
+/* Byte-slice front end with the reference's length checks, one hash:
+ * inputs[i] has lens[i] bytes.  Empty -> EMPTY_INPUT, any other length than 32
+ * -> INVALID_INPUT_LENGTH (validate_bytes_length + bytes_to_prime_field_element,
+ * poseidon.rs:255-300); n_inputs != width-1 cannot happen here by construction. */
+int inf_poseidon_hash_bytes(inf_ctx* ctx, uint32_t flags, const uint8_t* domain_tag,
+                            const uint8_t* const* inputs, const size_t* lens, uint32_t n_inputs,
+                            uint8_t out[32]);
+
+/* Same hash through the generic dense kernel (reference schedule taken
+ * literally, separate tables).  Diagnostic: lets callers cross-check the
+ * optimised kernels on the device. */
+int inf_poseidon_hash_batch_dense(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                                  const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
+                                  uint8_t* out);
+
+/* ---- Merkle zero tables -------------------------------------------------------
+ * get_merkle_zeroes(arity) (zeroes.rs:81-85): 33 x 32 bytes; arity 2 -> binary
+ * table, anything else -> quinary table.  EMPTY_BALLOT_ROOTS: 5 x 32 bytes. */
+int inf_merkle_zeroes(inf_ctx* ctx, uint32_t arity, uint8_t out[33 * 32]);
+int inf_empty_ballot_roots(uint8_t out[5 * 32]);
+
+/* ---- poll tree ------------------------------------------------------------------
+ * One-shot equivalent of
+ *     PollStateTree::new(arity, full_depth, zero_hash)        state.rs:142-170
+ *       .insert(leaf) for every leaf                          state.rs:176-225
+ *       .merge(to_depth)                                      state.rs:230-281
+ * over the full leaf array.
+ *   arity               2 or 5 (the two trees PollState::new builds, state.rs:42-67)
+ *   prepend_blank_leaf  non-zero: tree is seeded with zeroes[0] at leaf index 0,
+ *                       as the registration tree is (state.rs:48-52)
+ *   to_depth            merge's argument: pad with zero siblings up to full_depth
+ *   leaves              n_leaves * 32 bytes
+ * Outputs (any may be NULL):
+ *   root          32 bytes
+ *   insert_depth  PollStateTree.depth after the inserts (public signal
+ *                 actualStateTreeDepth, provider.rs:182)
+ *   root_depth    number of levels under root
+ * Errors: more leaves than arity^full_depth -> TREE_ALREADY_FULL (what insert
+ * returns); exactly arity^full_depth leaves -> TREE_ALREADY_MERGED (insert
+ * completed the tree, so merge refuses, state.rs:236); in that case `root`
+ * is still written so the caller can mirror `root: Some(..)`.  Zero leaves in
+ * total (no blank leaf either): root is left untouched, root_depth = 0 and the
+ * call returns INF_OK with *has_root = 0 (merge on an empty frontier leaves
+ * root = None, state.rs:240-248).
+ */
+int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                   int to_depth, const uint8_t* leaves, uint64_t n_leaves, uint8_t root[32],
+                   uint32_t* insert_depth, uint32_t* root_depth, int* has_root);
+/* Same with the leaves already in device memory; synchronises before return. */
+int inf_tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                       int to_depth, const void* d_leaves, uint64_t n_leaves, uint8_t root[32],
+                       uint32_t* insert_depth, uint32_t* root_depth, int* has_root, void* stream);
+
+/* Building block for sharded trees: reduce `n_in` consecutive nodes of level
+ * `level_in` (device memory) by `n_levels` levels, padding the right edge of
+ * level l with zeroes[l].  Writes ceil(n_in / arity^n_levels) nodes to d_out
+ * (device) and that count to *n_out.  Enqueued on `stream`; does not
+ * synchronise.  d_out may alias nothing; scratch is owned by the context. */
+int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,
+                        const void* d_in, uint64_t n_in, void* d_out, uint64_t* n_out,
+                        void* stream);
+
+/* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
+ * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */
+int inf_merge_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* leaves,
+                            uint64_t n_leaves, uint8_t root[32], uint8_t process_commitment[32],
+                            uint32_t* insert_depth);
+/* merge_interactions (provider.rs:313-327): inf_tree_merge(5, depth, 0, 1, ..)
+ * plus the expected proof counts. */
+int inf_merge_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8_t* leaves,
+                           uint64_t n_leaves, uint32_t registrations_count,
+                           uint32_t process_subtree_depth, uint32_t tally_subtree_depth,
+                           uint8_t root[32], int* has_root, uint32_t* expected_process,
+                           uint32_t* expected_tally);
+
+/* ---- diagnostics ---------------------------------------------------------------- */
+/* The round constants and MDS matrix for width t as canonical little-endian
+ * 32-bit limbs, ark ((8+RP)*t elements) then mds (t*t): exactly the numbers in
+ * parameters.rs for that width.  Returns the element count, or -1. */
+int inf_debug_dense_params(uint32_t t, uint32_t* out, size_t out_words);
+/* The optimised device table for width t (2..8).  Returns word count or -1. */
+int inf_debug_opt_table(uint32_t t, uint32_t* out, size_t out_words);
+/* Sustained 32-bit IMAD issue rate of the device, measured with independent
+ * multiply-add chains on every SM sub-partition.  kind 0: IMAD (lo), kind 1:
+ * IMAD.WIDE.U32 counted as 2 IMAD-equivalents each.  Result in IMAD/s. */
+int inf_measure_imad_peak(inf_ctx* ctx, int kind, double* imad_per_s, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFIMUM_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI declared in include/infimum_b200.h.
+
+This module is plumbing: it loads libinfimum_b200.so (built in-tree by
+infimum_b200.build) and declares argument types.  There is no fallback of any
+kind: if the library is missing, or no CUDA device is usable, it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libinfimum_b200.so")
+
+# return codes (include/infimum_b200.h)
+OK = 0
+ERR_TREE_ALREADY_FULL = 1
+ERR_TREE_ALREADY_MERGED = 2
+ERR_HASH_FAILED = 3
+ERR_MERGE_FAILED = 4
+ERR_INVALID_NUMBER_OF_INPUTS = 16
+ERR_EMPTY_INPUT = 17
+ERR_INVALID_INPUT_LENGTH = 18
+ERR_INVALID_WIDTH_CIRCOM = 19
+ERR_NULL_POINTER = 24
+ERR_BAD_ARITY = 25
+ERR_BAD_DEPTH = 26
+ERR_NO_DEVICE = 64
+ERR_CUDA = 65
+ERR_OUT_OF_MEMORY = 66
+FLAG_LITTLE_ENDIAN = 1
+
+# every symbol include/infimum_b200.h declares
+EXPORTS = [
+    "inf_init", "inf_destroy", "inf_strerror", "inf_last_cuda_error", "inf_version",
+    "inf_poseidon_hash_batch", "inf_poseidon_hash_batch_dev", "inf_poseidon_hash_bytes",
+    "inf_poseidon_hash_batch_dense", "inf_merkle_zeroes", "inf_empty_ballot_roots",
+    "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_merge_registrations",
+    "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
+    "inf_measure_imad_peak",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library (no GPU needed just to load and inspect symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "libinfimum_b200.so is not built (run `python -m infimum_b200.build`); "
+            "infimum_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    u8p, u32p, u64p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p
+    ip = C.POINTER(C.c_int)
+    lib.inf_init.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.inf_init.restype = C.c_int
+    lib.inf_destroy.argtypes = [vp]
+    lib.inf_destroy.restype = None
+    lib.inf_strerror.argtypes = [C.c_int]
+    lib.inf_strerror.restype = C.c_char_p
+    lib.inf_last_cuda_error.argtypes = [vp]
+    lib.inf_last_cuda_error.restype = C.c_char_p
+    lib.inf_version.argtypes = []
+    lib.inf_version.restype = C.c_char_p
+    lib.inf_poseidon_hash_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp]
+    lib.inf_poseidon_hash_batch.restype = C.c_int
+    lib.inf_poseidon_hash_batch_dense.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp]
+    lib.inf_poseidon_hash_batch_dense.restype = C.c_int
+    lib.inf_poseidon_hash_batch_dev.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, vp]
+    lib.inf_poseidon_hash_batch_dev.restype = C.c_int
+    lib.inf_poseidon_hash_bytes.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                            C.c_uint32, vp]
+    lib.inf_poseidon_hash_bytes.restype = C.c_int
+    lib.inf_merkle_zeroes.argtypes = [vp, C.c_uint32, vp]
+    lib.inf_merkle_zeroes.restype = C.c_int
+    lib.inf_empty_ballot_roots.argtypes = [vp]
+    lib.inf_empty_ballot_roots.restype = C.c_int
+    lib.inf_tree_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint64, vp, u32p, u32p, ip]
+    lib.inf_tree_merge.restype = C.c_int
+    lib.inf_tree_merge_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint64, vp, u32p,
+                                       u32p, ip, vp]
+    lib.inf_tree_merge_dev.restype = C.c_int
+    lib.inf_tree_reduce_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, u64p, vp]
+    lib.inf_tree_reduce_dev.restype = C.c_int
+    lib.inf_merge_registrations.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, u32p]
+    lib.inf_merge_registrations.restype = C.c_int
+    lib.inf_merge_interactions.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           vp, ip, u32p, u32p]
+    lib.inf_merge_interactions.restype = C.c_int
+    lib.inf_debug_dense_params.argtypes = [C.c_uint32, u32p, C.c_size_t]
+    lib.inf_debug_dense_params.restype = C.c_int
+    lib.inf_debug_opt_table.argtypes = [C.c_uint32, u32p, C.c_size_t]
+    lib.inf_debug_opt_table.restype = C.c_int
+    lib.inf_measure_imad_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.inf_measure_imad_peak.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def strerror(code: int) -> str:
+    return load().inf_strerror(code).decode()

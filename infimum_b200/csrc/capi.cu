@@ -1,0 +1,515 @@
+// C ABI of the library (include/infimum_b200.h): argument checking, the
+// reference's error semantics, device memory staging and the level-by-level
+// orchestration of the tree kernels.  No arithmetic happens on the host here —
+// hashes are only ever computed by the kernels.
+#include "infimum_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_params.h"
+#include "launch.h"
+#include "poseidon.cuh"
+
+namespace inf {
+cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double* clock_mhz,
+                             cudaStream_t st);
+}
+
+using namespace inf;
+
+struct inf_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    void* scratch[2] = {nullptr, nullptr};
+    size_t scratch_bytes[2] = {0, 0};
+    void* io[2] = {nullptr, nullptr};          // staging for host-buffer calls
+    size_t io_bytes[2] = {0, 0};
+    uint32_t* d_dense[14] = {};
+    uint8_t zeroes[2][33][32];                 // [0] binary, [1] quinary (zeroes.rs)
+    std::string last_cuda_error;
+};
+
+namespace {
+
+int cuda_fail(inf_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) {
+        ctx->last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    return e == cudaErrorMemoryAllocation ? INF_ERR_OUT_OF_MEMORY : INF_ERR_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+int grow(inf_ctx* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return INF_OK;
+    if (*p) {
+        CU(cudaFree(*p));
+        *p = nullptr;
+        *have = 0;
+    }
+    // round up so that repeated slightly-larger calls do not reallocate
+    size_t cap = std::max<size_t>(need, 1 << 20);
+    cap = (cap + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    CU(cudaMalloc(p, cap));
+    *have = cap;
+    return INF_OK;
+}
+
+struct Bind {
+    int dev_prev = -1;
+    bool ok = false;
+    explicit Bind(inf_ctx* ctx) {
+        if (cudaGetDevice(&dev_prev) != cudaSuccess) dev_prev = -1;
+        ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~Bind() {
+        if (dev_prev >= 0) cudaSetDevice(dev_prev);
+    }
+};
+
+typedef cudaError_t (*upload_fn)(const uint32_t*, size_t);
+typedef cudaError_t (*hash_fn)(const void*, void*, uint64_t, const TagArg&, bool, cudaStream_t);
+
+upload_fn uploaders[9] = {nullptr, nullptr, upload_table_t2, upload_table_t3, upload_table_t4,
+                          upload_table_t5, upload_table_t6, upload_table_t7, upload_table_t8};
+hash_fn hashers[9] = {nullptr, nullptr, launch_hash_batch_t2, launch_hash_batch_t3,
+                      launch_hash_batch_t4, launch_hash_batch_t5, launch_hash_batch_t6,
+                      launch_hash_batch_t7, launch_hash_batch_t8};
+
+TagArg make_tag(const uint8_t* tag) {
+    TagArg t;
+    memset(&t, 0, sizeof t);
+    if (tag) {
+        memcpy(t.w, tag, 32);
+        t.has = 1;
+    }
+    return t;
+}
+
+cudaError_t launch_level(uint32_t arity, const void* in, uint64_t shift, uint64_t n_in, void* out,
+                         uint64_t n_out, const uint8_t* zero, cudaStream_t st) {
+    return arity == 2 ? launch_tree_level_t3(in, shift, n_in, out, n_out, zero, st)
+                      : launch_tree_level_t6(in, shift, n_in, out, n_out, zero, st);
+}
+
+// arity^e saturating at 2^64-1
+uint64_t pow_sat(uint64_t a, uint32_t e) {
+    unsigned __int128 r = 1;
+    for (uint32_t i = 0; i < e; i++) {
+        r *= a;
+        if (r > (unsigned __int128)UINT64_MAX) return UINT64_MAX;
+    }
+    return (uint64_t)r;
+}
+
+int hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
+                   const void* d_in, uint64_t n, void* d_out, cudaStream_t st, bool dense) {
+    const uint32_t t = n_inputs + 1;
+    const bool le = flags & INF_FLAG_LITTLE_ENDIAN;
+    const TagArg ta = make_tag(tag);
+    if (!dense && t <= 8) {
+        CU(hashers[t](d_in, d_out, n, ta, le, st));
+    } else {
+        CU(launch_hash_dense((int)t, ctx->d_dense[t], d_in, d_out, n, ta, le, st));
+    }
+    return INF_OK;
+}
+
+int check_hash_args(inf_ctx* ctx, uint32_t n_inputs, const void* in, uint64_t n, void* out) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    // new_circom: width = n_inputs + 1 must be in 2..13 (poseidon.rs:315-320,
+    // parameters.rs:38-42)
+    if (n_inputs < 1 || n_inputs + 1 > 13) return INF_ERR_INVALID_WIDTH_CIRCOM;
+    if (n && (!in || !out)) return INF_ERR_NULL_POINTER;
+    return INF_OK;
+}
+
+// Core of the tree merge on device-resident leaves.  Leaves the root (if any)
+// in host memory.  `st` is synchronised before return.
+int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank, int to_depth,
+                   const void* d_leaves, uint64_t n_leaves, uint8_t* root, uint32_t* insert_depth,
+                   uint32_t* root_depth, int* has_root, cudaStream_t st) {
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    if (n_leaves && !d_leaves) return INF_ERR_NULL_POINTER;
+    const uint64_t shift = blank ? 1 : 0;
+    const uint64_t n_total = n_leaves + shift;
+    const uint64_t cap = pow_sat(arity, full_depth);
+    if (insert_depth) *insert_depth = 0;
+    if (root_depth) *root_depth = 0;
+    if (has_root) *has_root = 0;
+    if (n_total > cap) return INF_ERR_TREE_ALREADY_FULL;          // insert(): state.rs:182
+    if (n_total == 0) return INF_OK;                              // merge() on an empty frontier
+    // depth reached by insert(): largest d with arity^d <= n_total (state.rs:212-213)
+    uint32_t idepth = 0;
+    while (idepth < full_depth && pow_sat(arity, idepth + 1) <= n_total) idepth++;
+    // levels under the root
+    uint32_t rdepth;
+    const bool completed_by_insert = (n_total == cap);           // state.rs:218-222
+    if (to_depth || completed_by_insert) {
+        rdepth = full_depth;
+    } else {
+        rdepth = 0;
+        while (pow_sat(arity, rdepth) < n_total) rdepth++;
+    }
+    if (insert_depth) *insert_depth = idepth;
+    if (root_depth) *root_depth = rdepth;
+
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    uint8_t root_local[32];
+    if (rdepth == 0) {
+        // single node: the blank leaf itself, or the only leaf
+        if (blank) memcpy(root_local, Z[0], 32);
+        else CU(cudaMemcpyAsync(root_local, d_leaves, 32, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    } else {
+        const uint64_t n1 = (n_total + arity - 1) / arity;
+        const uint64_t n2 = (n1 + arity - 1) / arity;
+        int rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32);
+        if (rc) return rc;
+        rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32);
+        if (rc) return rc;
+        const void* cur = d_leaves;
+        uint64_t n_cur = n_leaves, sh = shift;
+        for (uint32_t l = 0; l < rdepth; l++) {
+            const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
+            void* dst = ctx->scratch[l & 1];
+            CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[l], st));
+            cur = dst;
+            n_cur = n_next;
+            sh = 0;
+        }
+        CU(cudaMemcpyAsync(root_local, cur, 32, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (root) memcpy(root, root_local, 32);
+    if (has_root) *has_root = 1;
+    return completed_by_insert ? INF_ERR_TREE_ALREADY_MERGED : INF_OK;   // merge(): state.rs:236
+}
+
+std::mutex g_init_mu;
+
+}  // namespace
+
+extern "C" {
+
+const char* inf_version(void) { return "infimum_b200 0.1 (sm_100a)"; }
+
+const char* inf_strerror(int code) {
+    switch (code) {
+        case INF_OK: return "ok";
+        case INF_ERR_TREE_ALREADY_FULL: return "MerkleTreeError::TreeAlreadyFull";
+        case INF_ERR_TREE_ALREADY_MERGED: return "MerkleTreeError::TreeAlreadyMerged";
+        case INF_ERR_HASH_FAILED: return "MerkleTreeError::HashFailed";
+        case INF_ERR_MERGE_FAILED: return "MerkleTreeError::MergeFailed";
+        case INF_ERR_INVALID_NUMBER_OF_INPUTS: return "PoseidonError::InvalidNumberOfInputs";
+        case INF_ERR_EMPTY_INPUT: return "PoseidonError::EmptyInput";
+        case INF_ERR_INVALID_INPUT_LENGTH: return "PoseidonError::InvalidInputLength";
+        case INF_ERR_INVALID_WIDTH_CIRCOM: return "PoseidonError::InvalidWidthCircom";
+        case INF_ERR_NULL_POINTER: return "null pointer argument";
+        case INF_ERR_BAD_ARITY: return "arity must be 2 or 5";
+        case INF_ERR_BAD_DEPTH: return "tree depth exceeds the 33-level zero table";
+        case INF_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case INF_ERR_CUDA: return "CUDA error (see inf_last_cuda_error)";
+        case INF_ERR_OUT_OF_MEMORY: return "device out of memory";
+        default: return "unknown error code";
+    }
+}
+
+const char* inf_last_cuda_error(const inf_ctx* ctx) { return ctx ? ctx->last_cuda_error.c_str() : ""; }
+
+int inf_init(int device, inf_ctx** out) {
+    if (!out) return INF_ERR_NULL_POINTER;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return INF_ERR_NO_DEVICE;
+    }
+    std::lock_guard<std::mutex> lock(g_init_mu);
+    inf_ctx* ctx = new inf_ctx();
+    ctx->device = device;
+    Bind bind(ctx);
+    auto fail = [&](int rc) {
+        inf_destroy(ctx);
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return fail(cuda_fail(nullptr, e, "cudaDeviceGetAttribute"));
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(cuda_fail(nullptr, e, "cudaStreamCreate"));
+    try {
+        for (int t = 2; t <= 8; t++) {
+            std::vector<uint32_t> tbl = host::build_opt_table(t);
+            if ((e = uploaders[t](tbl.data(), tbl.size())) != cudaSuccess)
+                return fail(cuda_fail(nullptr, e, "upload optimised table"));
+        }
+        for (int t = 2; t <= 13; t++) {
+            std::vector<uint32_t> tbl = host::build_dense_table(t);
+            if ((e = cudaMalloc((void**)&ctx->d_dense[t], tbl.size() * 4)) != cudaSuccess)
+                return fail(cuda_fail(nullptr, e, "cudaMalloc dense table"));
+            if ((e = cudaMemcpy(ctx->d_dense[t], tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+                return fail(cuda_fail(nullptr, e, "cudaMemcpy dense table"));
+        }
+    } catch (const std::exception&) {
+        return fail(INF_ERR_HASH_FAILED);
+    }
+    // Zero tables: Z[l+1] = H(Z[l] x arity), 32 links each, hashed on the device.
+    {
+        void* d = nullptr;
+        if ((e = cudaMalloc(&d, 6 * 32)) != cudaSuccess) return fail(cuda_fail(nullptr, e, "cudaMalloc"));
+        for (int a = 0; a < 2; a++) {
+            const int arity = a == 0 ? 2 : 5;
+            memcpy(ctx->zeroes[a][0], a == 0 ? host::BINARY_ZERO_LEAF_BE : host::QUINARY_ZERO_LEAF_BE, 32);
+            for (int l = 0; l < 32 && e == cudaSuccess; l++) {
+                uint8_t in[5 * 32];
+                for (int k = 0; k < arity; k++) memcpy(in + 32 * k, ctx->zeroes[a][l], 32);
+                e = cudaMemcpyAsync(d, in, arity * 32, cudaMemcpyHostToDevice, ctx->stream);
+                if (e == cudaSuccess) e = hashers[arity + 1](d, (char*)d + 5 * 32, 1, make_tag(nullptr), false, ctx->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->zeroes[a][l + 1], (char*)d + 5 * 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            }
+        }
+        cudaFree(d);
+        if (e != cudaSuccess) return fail(cuda_fail(nullptr, e, "zero-table chain"));
+    }
+    *out = ctx;
+    return INF_OK;
+}
+
+void inf_destroy(inf_ctx* ctx) {
+    if (!ctx) return;
+    {
+        Bind bind(ctx);
+        for (int i = 0; i < 2; i++) {
+            if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+            if (ctx->io[i]) cudaFree(ctx->io[i]);
+        }
+        for (int t = 0; t < 14; t++)
+            if (ctx->d_dense[t]) cudaFree(ctx->d_dense[t]);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                                const uint8_t* domain_tag, const void* d_in, uint64_t n,
+                                void* d_out, void* stream) {
+    int rc = check_hash_args(ctx, n_inputs, d_in, n, d_out);
+    if (rc) return rc;
+    Bind bind(ctx);
+    return hash_batch_dev(ctx, n_inputs, flags, domain_tag, d_in, n, d_out,
+                          stream ? (cudaStream_t)stream : ctx->stream, false);
+}
+
+static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
+                           const uint8_t* in, uint64_t n, uint8_t* out, bool dense) {
+    int rc = check_hash_args(ctx, n_inputs, in, n, out);
+    if (rc) return rc;
+    if (n == 0) return INF_OK;
+    Bind bind(ctx);
+    const size_t in_bytes = (size_t)n * n_inputs * 32, out_bytes = (size_t)n * 32;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], in_bytes))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], out_bytes))) return rc;
+    CU(cudaMemcpyAsync(ctx->io[0], in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, ctx->io[0], n, ctx->io[1], ctx->stream, dense)))
+        return rc;
+    CU(cudaMemcpyAsync(out, ctx->io[1], out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return INF_OK;
+}
+
+int inf_poseidon_hash_batch(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                            const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
+                            uint8_t* out) {
+    return hash_batch_host(ctx, n_inputs, flags, domain_tag, in, n, out, false);
+}
+
+int inf_poseidon_hash_batch_dense(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
+                                  const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
+                                  uint8_t* out) {
+    return hash_batch_host(ctx, n_inputs, flags, domain_tag, in, n, out, true);
+}
+
+int inf_poseidon_hash_bytes(inf_ctx* ctx, uint32_t flags, const uint8_t* domain_tag,
+                            const uint8_t* const* inputs, const size_t* lens, uint32_t n_inputs,
+                            uint8_t out[32]) {
+    if (!ctx || !out || (n_inputs && (!inputs || !lens))) return INF_ERR_NULL_POINTER;
+    if (n_inputs < 1 || n_inputs + 1 > 13) return INF_ERR_INVALID_WIDTH_CIRCOM;
+    uint8_t buf[12 * 32];
+    for (uint32_t i = 0; i < n_inputs; i++) {
+        // validate_bytes_length (poseidon.rs:255-273) then the exact-length
+        // check of bytes_to_prime_field_element (poseidon.rs:282-288), in the
+        // order the iterator applies them: first failing input wins.
+        if (lens[i] == 0) return INF_ERR_EMPTY_INPUT;
+        if (lens[i] != 32) return INF_ERR_INVALID_INPUT_LENGTH;
+        if (!inputs[i]) return INF_ERR_NULL_POINTER;
+        memcpy(buf + 32 * i, inputs[i], 32);
+    }
+    return hash_batch_host(ctx, n_inputs, flags, domain_tag, buf, 1, out, false);
+}
+
+int inf_merkle_zeroes(inf_ctx* ctx, uint32_t arity, uint8_t out[33 * 32]) {
+    if (!ctx || !out) return INF_ERR_NULL_POINTER;
+    memcpy(out, ctx->zeroes[arity == 2 ? 0 : 1], 33 * 32);
+    return INF_OK;
+}
+
+int inf_empty_ballot_roots(uint8_t out[5 * 32]) {
+    if (!out) return INF_ERR_NULL_POINTER;
+    memcpy(out, host::EMPTY_BALLOT_ROOTS_BE, 5 * 32);
+    return INF_OK;
+}
+
+int inf_tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                       int to_depth, const void* d_leaves, uint64_t n_leaves, uint8_t root[32],
+                       uint32_t* insert_depth, uint32_t* root_depth, int* has_root, void* stream) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, d_leaves, n_leaves,
+                          root, insert_depth, root_depth, has_root,
+                          stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                   int to_depth, const uint8_t* leaves, uint64_t n_leaves, uint8_t root[32],
+                   uint32_t* insert_depth, uint32_t* root_depth, int* has_root) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n_leaves && !leaves) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    Bind bind(ctx);
+    // capacity check before moving any data (insert would have failed first)
+    if (n_leaves + (prepend_blank_leaf ? 1 : 0) > pow_sat(arity, full_depth)) {
+        if (insert_depth) *insert_depth = 0;
+        if (root_depth) *root_depth = 0;
+        if (has_root) *has_root = 0;
+        return INF_ERR_TREE_ALREADY_FULL;
+    }
+    if (n_leaves) {
+        int rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->io[0], leaves, (size_t)n_leaves * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, ctx->io[0], n_leaves,
+                          root, insert_depth, root_depth, has_root, ctx->stream);
+}
+
+int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,
+                        const void* d_in, uint64_t n_in, void* d_out, uint64_t* n_out,
+                        void* stream) {
+    if (!ctx || !d_out) return INF_ERR_NULL_POINTER;
+    if (n_in && !d_in) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (level_in + n_levels > 32) return INF_ERR_BAD_DEPTH;
+    Bind bind(ctx);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    if (n_levels == 0) {
+        if (n_in) CU(cudaMemcpyAsync(d_out, d_in, (size_t)n_in * 32, cudaMemcpyDeviceToDevice, st));
+        if (n_out) *n_out = n_in;
+        return INF_OK;
+    }
+    if (n_in == 0) {
+        if (n_out) *n_out = 0;
+        return INF_OK;
+    }
+    const uint64_t n1 = (n_in + arity - 1) / arity;
+    const uint64_t n2 = (n1 + arity - 1) / arity;
+    int rc;
+    if (n_levels > 1 && (rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
+    if (n_levels > 2 && (rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
+    const void* cur = d_in;
+    uint64_t n_cur = n_in;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint64_t n_next = (n_cur + arity - 1) / arity;
+        void* dst = (l + 1 == n_levels) ? d_out : ctx->scratch[l & 1];
+        CU(launch_level(arity, cur, 0, n_cur, dst, n_next, Z[level_in + l], st));
+        cur = dst;
+        n_cur = n_next;
+    }
+    if (n_out) *n_out = n_cur;
+    return INF_OK;
+}
+
+int inf_merge_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* leaves,
+                            uint64_t n_leaves, uint8_t root[32], uint8_t process_commitment[32],
+                            uint32_t* insert_depth) {
+    if (!ctx || !root || !process_commitment) return INF_ERR_NULL_POINTER;
+    int has = 0;
+    uint32_t rdepth = 0;
+    // registrations.merge(false)  (provider.rs:293)
+    int rc = inf_tree_merge(ctx, 2, registration_depth, 1, 0, leaves, n_leaves, root, insert_depth,
+                            &rdepth, &has);
+    if (rc) return rc;
+    if (!has) return INF_ERR_MERGE_FAILED;                         // provider.rs:295
+    // commitment.process = (0, H3(root, EMPTY_BALLOT_ROOTS[1], 0))  (provider.rs:296-308)
+    uint8_t in[3 * 32];
+    memcpy(in, root, 32);
+    memcpy(in + 32, host::EMPTY_BALLOT_ROOTS_BE[1], 32);
+    memset(in + 64, 0, 32);
+    rc = inf_poseidon_hash_batch(ctx, 3, 0, nullptr, in, 1, process_commitment);
+    return rc ? INF_ERR_HASH_FAILED : INF_OK;
+}
+
+int inf_merge_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8_t* leaves,
+                           uint64_t n_leaves, uint32_t registrations_count,
+                           uint32_t process_subtree_depth, uint32_t tally_subtree_depth,
+                           uint8_t root[32], int* has_root, uint32_t* expected_process,
+                           uint32_t* expected_tally) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    uint32_t idepth = 0, rdepth = 0;
+    // interactions.merge(true)  (provider.rs:317)
+    int rc = inf_tree_merge(ctx, 5, interaction_depth, 0, 1, leaves, n_leaves, root, &idepth, &rdepth,
+                            has_root);
+    if (rc) return rc;
+    // provider.rs:319-324 (u32 arithmetic as in the reference)
+    const uint32_t count = (uint32_t)n_leaves;
+    const uint32_t pb = (uint32_t)pow_sat(5, process_subtree_depth);
+    const uint32_t tb = (uint32_t)pow_sat(2, tally_subtree_depth);
+    if (expected_process) *expected_process = pb ? count / pb + ((count % pb) ? 1u : 0u) : 0u;
+    if (expected_tally) *expected_tally = tb ? 1u + registrations_count / tb : 0u;
+    return INF_OK;
+}
+
+int inf_debug_dense_params(uint32_t t, uint32_t* out, size_t out_words) {
+    if (t < 2 || t > 13 || !out) return -1;
+    const host::DenseParams& d = host::grain_params((int)t);
+    const size_t n = d.ark.size() + d.mds.size();
+    if (out_words < n * 8) return -1;
+    size_t k = 0;
+    for (const host::F& x : d.ark) host::to_limbs32(x, out + 8 * k++);
+    for (const host::F& x : d.mds) host::to_limbs32(x, out + 8 * k++);
+    return (int)n;
+}
+
+int inf_debug_opt_table(uint32_t t, uint32_t* out, size_t out_words) {
+    if (t < 2 || t > 8 || !out) return -1;
+    std::vector<uint32_t> v = host::build_opt_table((int)t);
+    if (out_words < v.size()) return -1;
+    memcpy(out, v.data(), v.size() * 4);
+    return (int)v.size();
+}
+
+int inf_measure_imad_peak(inf_ctx* ctx, int kind, double* imad_per_s, double* sm_clock_mhz) {
+    if (!ctx || !imad_per_s) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    double clk = 0;
+    CU(launch_imad_peak(kind, ctx->sm_count, imad_per_s, &clk, ctx->stream));
+    if (sm_clock_mhz) *sm_clock_mhz = clk;
+    return INF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// Poseidon over BN254 Fr, circom parameters, one hash per thread.
+//
+// Computes exactly what `PoseidonHasher::hash` does
+// (pallet/src/hash/poseidon.rs:162-208: state = [tag, inputs...], 4 full
+// rounds, RP partial rounds, 4 full rounds of ARK -> x^5 -> MDS, output
+// state[0]) through an algebraically identical schedule:
+//
+//   * round constants folded into the matrix products (they ride along as the
+//     initial value of the lazy Montgomery accumulator, fr.cuh);
+//   * partial rounds in sparse form: the constants of the partial section are
+//     pushed forward until only a scalar on s[0] remains, and the dense MDS is
+//     factored so that a partial round costs 2t-1 products instead of t^2;
+//   * in the last round only row 0 of the MDS is evaluated (the reference
+//     discards the rest, poseidon.rs:205), against the non-Montgomery copy of
+//     that row, so the dot product lands directly on the canonical value.
+//
+// The tables are derived at library init from the Grain-LFSR constants
+// (host_params.cpp) and are cross-checked in the tests against an independent
+// Python derivation (tests/opt_model.py), which in turn is proven equal to
+// the dense reference algorithm.
+#pragma once
+#include "fr.cuh"
+
+namespace inf {
+
+// PARTIAL_ROUNDS[t-2], pallet/src/hash/parameters.rs:17-18
+INF_HD constexpr int partial_rounds(int t) {
+    return t == 2 ? 56 : t == 3 ? 57 : t == 4 ? 56 : t == 5 ? 60 : t == 6 ? 60 : t == 7 ? 63
+         : t == 8 ? 64 : t == 9 ? 63 : t == 10 ? 60 : t == 11 ? 66 : t == 12 ? 60 : 65;
+}
+
+// Table layout, in units of one field element (8 x u32).  All entries are
+// Montgomery form (x*R mod p) except the "V" entries, which are x*R^2 mod p
+// (they enter an accumulator that is then divided by R), and OUT_ROW, which is
+// canonical.
+template <int T>
+struct Layout {
+    static constexpr int RP = partial_rounds(T);
+    static constexpr int R2 = 0;                         // R^2 mod p
+    static constexpr int IN_V = R2 + 1;                  // [T]   C_0[i] * R^2
+    static constexpr int S0 = IN_V + T;                  // C_0[0] * R   (state[0] when tag == 0)
+    static constexpr int FULL_M = S0 + 1;                // [T][T] MDS
+    static constexpr int PRE_M = FULL_M + T * T;         // [T][T] MDS with the sparse prefix merged
+    static constexpr int FULL_V = PRE_M + T * T;         // [3][T] C_{r+1}, r = 0..2
+    static constexpr int PRE_V = FULL_V + 3 * T;         // [T]   (k_0, 0, ..., 0)
+    static constexpr int PART = PRE_V + T;               // [RP][2T]: row0[T], w[T-1], kv
+    static constexpr int PART_STRIDE = 2 * T;
+    static constexpr int LAST_D = PART + RP * PART_STRIDE;   // [T-1]  D[1..] * R (added once)
+    static constexpr int TAIL_V = LAST_D + (T - 1);      // [3][T] C_{4+RP+r+1}, r = 0..2
+    static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
+    static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
+    static constexpr int COUNT = OUT_ROW_MONT + T;
+    static constexpr int WORDS = COUNT * 8;
+};
+
+// out = ( sum_j a[j] * tbl[b_off + j] + tbl[v_off] ) / R, then the cheap range step.
+template <int N, int STRIDE_A>
+INF_HD void dot(uint32_t (&out)[8], const uint32_t* a, const uint32_t* b, const uint32_t* v) {
+    MontAcc acc;
+    if (v) acc.init(v); else acc.zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) acc.row(i, a + j * STRIDE_A, b[j * 8 + i]);
+        acc.reduce(i);
+    }
+    acc.finish(out);
+    csub2p(out);
+}
+
+// x^5
+INF_HD void sbox(uint32_t (&y)[8], const uint32_t (&x)[8]) {
+    uint32_t x2[8], x4[8];
+    mont_mul(x2, x, x);
+    mont_mul(x4, x2, x2);
+    mont_mul(y, x4, x);
+}
+
+// The permutation proper.  On entry s = [tag, inputs...] + C_0 in Montgomery
+// form, every element < 2p + eps.  On return `out` holds state[0] after the
+// last round: canonical integer in [0, p) if !MONT_OUT, Montgomery form
+// (< 2p + eps) if MONT_OUT.
+template <int T, bool MONT_OUT>
+INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint32_t* tbl) {
+    using L = Layout<T>;
+    static_assert(T >= 2 && T <= 8, "optimised path covers widths 2..8");
+    uint32_t x[T][8];
+
+    // ---- first half: rounds 0..3 (round 3 uses the merged matrix) ----------
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::PRE_M) * 8;
+        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::PRE_V) * 8;
+#pragma unroll
+        for (int i = 0; i < T; i++) sbox(x[i], s[i]);
+#pragma unroll
+        for (int i = 0; i < T; i++) dot<T, 8>(s[i], &x[0][0], m + i * T * 8, v + i * 8);
+    }
+
+    // ---- partial rounds -----------------------------------------------------
+#pragma unroll 1
+    for (int j = 0; j < L::RP; j++) {
+        const uint32_t* pt = tbl + (L::PART + j * L::PART_STRIDE) * 8;
+        sbox(x[0], s[0]);
+        // element 0 temporarily holds the S-box output so that the dot runs
+        // over the contiguous state
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[0][k] = x[0][k];
+        uint32_t n0[8];
+        dot<T, 8>(n0, &s[0][0], pt, pt + (2 * T - 1) * 8);
+#pragma unroll
+        for (int i = 1; i < T; i++) {
+            uint32_t w[8];
+            mont_mul(w, x[0], pt + (T + i - 1) * 8);
+            add8(s[i], s[i], w);
+            csub2p(s[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[0][k] = n0[k];
+    }
+    // remaining constants of the first tail round on elements 1..T-1
+#pragma unroll
+    for (int i = 1; i < T; i++) {
+        add8(s[i], s[i], tbl + (L::LAST_D + i - 1) * 8);
+        csub2p(s[i]);
+    }
+
+    // ---- second half: 3 full rounds, then the output row --------------------
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+        const uint32_t* m = tbl + L::FULL_M * 8;
+        const uint32_t* v = tbl + (L::TAIL_V + r * T) * 8;
+#pragma unroll
+        for (int i = 0; i < T; i++) sbox(x[i], s[i]);
+#pragma unroll
+        for (int i = 0; i < T; i++) dot<T, 8>(s[i], &x[0][0], m + i * T * 8, v + i * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < T; i++) sbox(x[i], s[i]);
+    if (MONT_OUT) {
+        dot<T, 8>(out, &x[0][0], tbl + L::OUT_ROW_MONT * 8, nullptr);
+    } else {
+        dot<T, 8>(out, &x[0][0], tbl + L::OUT_ROW * 8, nullptr);
+        csub_p_exact(out);
+        csub_p_exact(out);
+    }
+}
+
+// Raw 256-bit integer (little-endian limbs, any value < 2^256) -> element i of
+// the initial state, first round constant included:  (x + C_0[i]) * R mod p.
+template <int T>
+INF_HD void absorb(uint32_t (&s)[8], const uint32_t (&raw)[8], int i, const uint32_t* tbl) {
+    using L = Layout<T>;
+    MontAcc acc;
+    acc.init(tbl + (L::IN_V + i) * 8);
+    const uint32_t* r2 = tbl + L::R2 * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        acc.row(k, raw, r2[k]);
+        acc.reduce(k);
+    }
+    acc.finish(s);
+    // (0.189 * 5.29 + 1) p < 2p: already in range
+}
+
+// 32-byte wire format (pallet/src/poll/poll.rs:9 `HashBytes`, big-endian; the
+// little-endian variant serves hash_bytes_le, poseidon.rs:233-250) <-> limbs.
+// w[] are the eight 32-bit words as loaded from memory.
+INF_HD uint32_t bswap32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+template <bool LE>
+INF_HD void words_to_limbs(uint32_t (&limb)[8], const uint32_t (&w)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) limb[k] = LE ? w[k] : bswap32(w[7 - k]);
+}
+template <bool LE>
+INF_HD void limbs_to_words(uint32_t (&w)[8], const uint32_t (&limb)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = LE ? limb[k] : bswap32(limb[7 - k]);
+}
+
+// One complete hash: in_words = (T-1) x 8 words (wire order), tag_words = 8
+// words or nullptr (domain tag 0, poseidon.rs:304-307), out_words = 8 words.
+template <int T, bool LE>
+INF_HD void hash_words(uint32_t (&out_words)[8], const uint32_t (&in_words)[T - 1][8],
+                       const uint32_t* tag_words, const uint32_t* tbl) {
+    using L = Layout<T>;
+    uint32_t s[T][8];
+    if (tag_words) {
+        uint32_t w[8], raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = tag_words[k];
+        words_to_limbs<LE>(raw, w);
+        absorb<T>(s[0], raw, 0, tbl);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[0][k] = tbl[L::S0 * 8 + k];
+    }
+#pragma unroll
+    for (int i = 1; i < T; i++) {
+        uint32_t raw[8];
+        words_to_limbs<LE>(raw, in_words[i - 1]);
+        absorb<T>(s[i], raw, i, tbl);
+    }
+    uint32_t h[8];
+    poseidon_rounds<T, false>(h, s, tbl);
+    limbs_to_words<LE>(out_words, h);
+}
+
+}  // namespace inf

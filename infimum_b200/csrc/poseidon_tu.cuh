@@ -1,0 +1,113 @@
+// Per-width translation unit body.  Each poseidon_tN.cu defines INF_T and
+// includes this file, so that every width has its own 64 KB __constant__ bank
+// for its table (Layout<T>) and the widths compile in parallel.
+//
+// Kernels (one hash per thread; the path is bound by the integer-multiply
+// pipe, ~2300 IMAD per byte moved, so memory layout only has to be sane:
+// each thread moves whole 32-byte sectors with 128-bit loads/stores):
+//   hash_batch_kernel   n x (T-1) x 32 B  ->  n x 32 B        K1 in SURVEY.md
+//   tree_level_kernel   one tree level, arity T-1, zero padded  K2
+#include <cuda_runtime.h>
+
+#include "launch.h"
+#include "poseidon.cuh"
+
+#ifndef INF_T
+#error "define INF_T before including poseidon_tu.cuh"
+#endif
+
+namespace inf {
+namespace {
+
+constexpr int T = INF_T;
+__constant__ uint32_t c_tbl[Layout<T>::WORDS];
+
+struct Node32 {
+    uint32_t w[8];
+};
+
+__device__ __forceinline__ void load_node(uint32_t (&w)[8], const uint4* p) {
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <bool LE>
+__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS)
+hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_t n, TagArg tag) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    uint32_t iw[T - 1][8], ow[8];
+    const uint4* p = in + idx * (uint64_t)(2 * (T - 1));
+#pragma unroll
+    for (int i = 0; i < T - 1; i++) load_node(iw[i], p + 2 * i);
+    hash_words<T, LE>(ow, iw, tag.has ? tag.w : nullptr, c_tbl);
+    store_node(out + 2 * idx, ow);
+}
+
+// One level of an arity-(T-1) Merkle tree over big-endian 32-byte nodes.
+// The level's logical node array is `shift` copies of the zero value followed
+// by in[0..n_in): shift = 1 at level 0 of the registration tree, whose leaf 0
+// is the blank state leaf = zeroes[0] (state.rs:48-52), else 0.
+// out[i] = H(node[A*i], ..., node[A*i+A-1]); nodes past the end are the
+// level's zero value (PollStateTree::merge's right padding, state.rs:262-266).
+__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS)
+tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
+                  uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
+    constexpr int A = T - 1;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out) return;
+    uint32_t iw[A][8], ow[8];
+    const uint64_t first = idx * A;
+#pragma unroll
+    for (int i = 0; i < A; i++) {
+        const uint64_t j = first + i;
+        if (j >= shift && j - shift < n_in) {
+            load_node(iw[i], in + 2 * (j - shift));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) iw[i][k] = zero.w[k];
+        }
+    }
+    hash_words<T, false>(ow, iw, nullptr, c_tbl);
+    store_node(out + 2 * idx, ow);
+}
+
+}  // namespace
+
+// ---- host-side launchers for this width (C++ linkage, used by capi.cu) ------
+#define INF_CAT2(a, b) a##b
+#define INF_CAT(a, b) INF_CAT2(a, b)
+
+cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t words) {
+    if (words != (size_t)Layout<T>::WORDS) return cudaErrorInvalidValue;
+    return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
+}
+
+cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, uint64_t n,
+                                                const TagArg& tag, bool le, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    if (le)
+        hash_batch_kernel<true><<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+    else
+        hash_batch_kernel<false><<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+    return cudaGetLastError();
+}
+
+cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift, uint64_t n_in,
+                                                void* d_out, uint64_t n_out,
+                                                const uint8_t* zero_be, cudaStream_t st) {
+    if (n_out == 0) return cudaSuccess;
+    Node32 z;
+    memcpy(z.w, zero_be, 32);
+    const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
+    tree_level_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
+    return cudaGetLastError();
+}
+
+}  // namespace inf

@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference's Poseidon hasher interface, backed by the
+CUDA kernels through the C ABI.
+
+Same names, argument meaning and error behaviour as
+pallet/src/hash/poseidon.rs:
+    Poseidon::<Fr>::new_circom(nr_inputs)              :304-307
+    Poseidon::<Fr>::with_domain_tag_circom(n, tag)     :309-326
+    PoseidonHasher::hash(&[Fr])                        :162-208
+    PoseidonBytesHasher::hash_bytes_be / hash_bytes_le :213-250
+plus the batch forms the GPU exists for (`hash_batch*`).  Field elements are
+Python ints (canonical) at the `hash` level and 32-byte strings at the byte
+level.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .context import Context, get_context
+from .errors import PoseidonError
+
+# p, quoted at pallet/src/hash/parameters.rs:14
+MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+HASH_LEN = 32            # poseidon.rs:9
+MAX_X5_LEN = 13          # poseidon.rs:10
+
+
+def _as_u8(buf) -> np.ndarray:
+    a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    if a.dtype != np.uint8:
+        raise TypeError("expected bytes or a uint8 array")
+    return np.ascontiguousarray(a).reshape(-1)
+
+
+class Poseidon:
+    def __init__(self, nr_inputs: int, domain_tag: int = 0, ctx: Optional[Context] = None):
+        width = nr_inputs + 1
+        if width > MAX_X5_LEN or width < 2:                       # poseidon.rs:315-320, parameters.rs:38-42
+            raise PoseidonError("InvalidWidthCircom", width=width, max_limit=MAX_X5_LEN)
+        self.width = width
+        self.domain_tag = int(domain_tag) % MODULUS
+        self.ctx = ctx or get_context()
+
+    @classmethod
+    def new_circom(cls, nr_inputs: int, ctx: Optional[Context] = None) -> "Poseidon":
+        return cls(nr_inputs, 0, ctx)
+
+    @classmethod
+    def with_domain_tag_circom(cls, nr_inputs: int, domain_tag: int, ctx: Optional[Context] = None) -> "Poseidon":
+        return cls(nr_inputs, domain_tag, ctx)
+
+    # ---- single hash, reference signatures -----------------------------------
+    def hash(self, inputs: Sequence[int]) -> int:
+        """PoseidonHasher::hash: field elements in, field element out."""
+        if len(inputs) != self.width - 1:                         # poseidon.rs:164-171
+            raise PoseidonError("InvalidNumberOfInputs", inputs=len(inputs),
+                                max_limit=self.width - 1, width=self.width)
+        buf = b"".join((int(x) % MODULUS).to_bytes(32, "big") for x in inputs)
+        out = self.hash_batch(buf, 1)
+        return int.from_bytes(out.tobytes(), "big")
+
+    def _hash_bytes(self, inputs: Sequence[bytes], flags: int) -> bytes:
+        n = len(inputs)
+        if n != self.width - 1:
+            # the byte front ends convert every input first (so length errors
+            # win), then call hash(), which checks the count (poseidon.rs:215-226)
+            for b in inputs:
+                if len(b) == 0:
+                    raise PoseidonError("EmptyInput")
+                if len(b) != HASH_LEN:
+                    raise PoseidonError("InvalidInputLength", len=len(b), modulus_bytes_len=HASH_LEN)
+            raise PoseidonError("InvalidNumberOfInputs", inputs=n, max_limit=self.width - 1, width=self.width)
+        ptrs = (C.c_char_p * n)(*[bytes(b) if len(b) else None for b in inputs])
+        lens = (C.c_size_t * n)(*[len(b) for b in inputs])
+        out = C.create_string_buffer(32)
+        tag = self._tag_bytes(flags)
+        rc = self.ctx.lib.inf_poseidon_hash_bytes(self.ctx.handle, flags, tag, ptrs, lens, n, out)
+        self.ctx.check(rc)
+        return out.raw
+
+    def hash_bytes_be(self, inputs: Sequence[bytes]) -> bytes:
+        return self._hash_bytes(inputs, 0)
+
+    def hash_bytes_le(self, inputs: Sequence[bytes]) -> bytes:
+        return self._hash_bytes(inputs, _lib.FLAG_LITTLE_ENDIAN)
+
+    # ---- batch forms -----------------------------------------------------------
+    def _tag_bytes(self, flags: int):
+        if self.domain_tag == 0:
+            return None
+        return self.domain_tag.to_bytes(32, "little" if flags & _lib.FLAG_LITTLE_ENDIAN else "big")
+
+    def hash_batch(self, inputs, n: Optional[int] = None, little_endian: bool = False,
+                   dense: bool = False) -> np.ndarray:
+        """n independent hashes.  `inputs`: bytes / uint8 array of n*(width-1)*32
+        bytes (host memory).  Returns an (n, 32) uint8 array."""
+        a = _as_u8(inputs)
+        k = self.width - 1
+        if n is None:
+            if a.size % (k * 32):
+                raise PoseidonError("InvalidInputLength", len=a.size, modulus_bytes_len=HASH_LEN)
+            n = a.size // (k * 32)
+        if a.size != n * k * 32:
+            raise PoseidonError("InvalidInputLength", len=a.size, modulus_bytes_len=HASH_LEN)
+        out = np.empty((n, 32), dtype=np.uint8)
+        flags = _lib.FLAG_LITTLE_ENDIAN if little_endian else 0
+        fn = self.ctx.lib.inf_poseidon_hash_batch_dense if dense else self.ctx.lib.inf_poseidon_hash_batch
+        rc = fn(self.ctx.handle, k, flags, self._tag_bytes(flags), a.ctypes.data, n, out.ctypes.data)
+        self.ctx.check(rc)
+        return out
+
+    def hash_batch_device(self, d_in: int, n: int, d_out: int, stream: int = 0, little_endian: bool = False):
+        """Same on device pointers (ints); enqueued on `stream` (a cudaStream_t
+        value, 0 = the context's stream); does not synchronise."""
+        flags = _lib.FLAG_LITTLE_ENDIAN if little_endian else 0
+        rc = self.ctx.lib.inf_poseidon_hash_batch_dev(self.ctx.handle, self.width - 1, flags,
+                                                      self._tag_bytes(flags), d_in, n, d_out, stream or None)
+        self.ctx.check(rc)
+
+
+def validate_bytes_length(b: bytes) -> None:
+    """poseidon.rs:255-273"""
+    if len(b) == 0:
+        raise PoseidonError("EmptyInput")
+    if len(b) > HASH_LEN:
+        raise PoseidonError("InvalidInputLength", len=len(b), modulus_bytes_len=HASH_LEN)

@@ -1,0 +1,111 @@
+"""Python model of the optimised Poseidon schedule the CUDA kernels run.
+
+Test helper (lives beside the tests, imports the oracle): derives, from the
+reference's (C, M), the tables the library derives in C++ at init
+(infimum_b200/csrc/host_params.cpp) and evaluates the optimised schedule on
+Python ints.  tests/test_opt_model.py checks model == dense oracle, and
+tests/test_capi_tables.py checks the library's tables == this model's.
+
+Schedule (exact field identities, so still bit-identical to
+pallet/src/hash/poseidon.rs:184-203):
+
+  s      = [tag, in...] + C_0
+  r=0..2 : s = M . sbox(s) + C_{r+1}
+  r=3    : s = PRE . sbox(s) + k_0 e0                     PRE = B_0 . M
+  j=0..RP-1 (partial): s0 = s0^5 ; s = S_j . s ; s0 += k_{j+1}   (last: s += D)
+  r=4+RP..7+RP : s = M . sbox(s) + C_{r+1}                (C_{8+RP} = 0)
+  out = s[0]
+
+k_j / D: round constants of the partial section pushed forward through M
+(valid because the partial S-box is the identity on elements 1..t-1).
+S_j = [[m00, v.Mhat^-1],[w, I]] and B_j = diag(1, Mhat) come from factoring
+N = S.B right to left through the partial rounds, each B commuting with the
+preceding partial S-box and merging into the previous round's matrix.
+"""
+from oracle.poseidon_ref import P, poseidon_parameters
+
+
+def _matmul(A, B):
+    n, m, k = len(A), len(B[0]), len(B)
+    return [[sum(A[i][x] * B[x][j] for x in range(k)) % P for j in range(m)] for i in range(n)]
+
+
+def _matvec(A, v):
+    return [sum(a * x for a, x in zip(row, v)) % P for row in A]
+
+
+def _inv(A):
+    n = len(A)
+    M = [list(r) + [1 if i == j else 0 for j in range(n)] for i, r in enumerate(A)]
+    for c in range(n):
+        piv = next(r for r in range(c, n) if M[r][c] % P)
+        M[c], M[piv] = M[piv], M[c]
+        iv = pow(M[c][c], P - 2, P)
+        M[c] = [x * iv % P for x in M[c]]
+        for r in range(n):
+            if r != c and M[r][c]:
+                f = M[r][c]
+                M[r] = [(x - f * y) % P for x, y in zip(M[r], M[c])]
+    return [r[n:] for r in M]
+
+
+def derive(t):
+    ark, mds, rf, rp = poseidon_parameters(t)
+    half = rf // 2
+    C = [list(ark[r * t:(r + 1) * t]) for r in range(rf + rp)]
+    M = [list(r) for r in mds]
+
+    # --- constant compression through the partial section -------------------
+    carry = [0] * t
+    k = []
+    for j in range(rp):
+        c = [(a + b) % P for a, b in zip(C[half + j], carry)]
+        k.append(c[0])
+        c[0] = 0
+        carry = _matvec(M, c)
+    D = [(a + b) % P for a, b in zip(C[half + rp], carry)]
+
+    # --- sparse factorisation, last partial round first ----------------------
+    sparse = [None] * rp
+    N = M
+    for j in reversed(range(rp)):
+        m00 = N[0][0]
+        v = N[0][1:]
+        w = [N[i][0] for i in range(1, t)]
+        Nhat = [row[1:] for row in N[1:]]
+        Ninv = _inv(Nhat)
+        vp = [sum(v[x] * Ninv[x][c] for x in range(t - 1)) % P for c in range(t - 1)]
+        sparse[j] = ([m00] + vp, w)                       # row 0, column 0 below the corner
+        B = [[1] + [0] * (t - 1)] + [[0] + Nhat[i] for i in range(t - 1)]
+        # B commutes with this round's partial S-box and "+k e0", so it slides
+        # back to just after the previous round's matrix: that round now
+        # applies M first and B second, i.e. the product B.M
+        N = _matmul(B, M)
+    PRE = N
+    return dict(t=t, rf=rf, rp=rp, C=C, M=M, PRE=PRE, k=k, D=D, sparse=sparse)
+
+
+def hash_opt(inputs, tag=0, tables=None):
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    rp, M, C = T["rp"], T["M"], T["C"]
+    sb = lambda x: pow(x, 5, P)
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    s = _matvec(T["PRE"], [sb(x) for x in s])
+    s[0] = (s[0] + T["k"][0]) % P
+    for j in range(rp):
+        row0, w = T["sparse"][j]
+        x0 = sb(s[0])
+        new0 = (row0[0] * x0 + sum(a * b for a, b in zip(row0[1:], s[1:]))) % P
+        s = [new0] + [(s[i] + w[i - 1] * x0) % P for i in range(1, t)]
+        if j + 1 < rp:
+            s[0] = (s[0] + T["k"][j + 1]) % P
+        else:
+            s = [(a + b) % P for a, b in zip(s, T["D"])]
+    for r in range(4 + rp, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(a + b) % P for a, b in zip(s, C[r + 1])]
+    return s[0]

@@ -1,0 +1,313 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+oracle and the reference's golden vectors.  Bit-exact everywhere (integer
+arithmetic mod p).  Names follow the reference's tests
+(pallet/src/tests/poseidon.rs, pallet/src/tests/extrinsics.rs)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import poseidon_ref as O
+from tests.util import EDGE_VALUES, P, be, random_fr_bytes
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import infimum_b200
+    infimum_b200.get_context(0)
+    return infimum_b200
+
+
+# ---- pallet/src/tests/poseidon.rs ------------------------------------------------
+def test_fr_one(ib, golden):
+    h = ib.Poseidon.new_circom(2)
+    for raw in (b"\x01", b"\x00\x01", b"\x00\x00\x01"):
+        x = int.from_bytes(raw, "big")
+        assert be(h.hash([x, x])) == H(golden["fr_one"]["expected_be"])
+
+
+def test_bytes_ones_twos(ib, golden):
+    g = golden["bytes_ones_twos"]
+    ins = [H(x) for x in g["inputs_be"]]
+    h = ib.Poseidon.new_circom(2)
+    assert be(h.hash([int.from_bytes(b, "big") % P for b in ins])) == H(g["expected_be"])
+    assert h.hash_bytes_be(ins) == H(g["expected_be"])
+    assert h.hash_bytes_le(ins) == H(g["expected_le"])
+
+
+def test_with_domain_tag(ib, golden):
+    g = golden["with_domain_tag"]
+    ins = [int.from_bytes(H(x), "big") % P for x in g["inputs_be"]]
+    assert be(ib.Poseidon.with_domain_tag_circom(2, 0).hash(ins)) == H(g["expected_tag_zero_be"])
+    tagged = ib.Poseidon.with_domain_tag_circom(2, 1).hash(ins)
+    assert be(tagged) != H(g["expected_tag_zero_be"])
+    assert tagged == O.Poseidon.with_domain_tag_circom(2, 1).hash(ins)
+    # byte front ends carry the tag too, in either wire order
+    raw = [H(x) for x in g["inputs_be"]]
+    assert ib.Poseidon.with_domain_tag_circom(2, 77).hash_bytes_be(raw) == \
+        O.Poseidon.with_domain_tag_circom(2, 77).hash_bytes_be(raw)
+    assert ib.Poseidon.with_domain_tag_circom(2, 77).hash_bytes_le(raw) == \
+        O.Poseidon.with_domain_tag_circom(2, 77).hash_bytes_le(raw)
+
+
+def test_fr_one_two(ib, golden):
+    assert ib.Poseidon.new_circom(2).hash([1, 2]).to_bytes(32, "little") == H(golden["fr_one_two"]["expected_le"])
+
+
+def test_random_input(ib, golden):
+    # both inputs >= p: the kernels must reduce like from_be_bytes_mod_order
+    g = golden["random_input"]
+    raw = b"".join(H(x) for x in g["inputs_be"])
+    out = ib.Poseidon.new_circom(2).hash_batch(raw, 1)
+    assert out.tobytes()[::-1] == H(g["expected_le"])
+
+
+def test_empty_input(ib):
+    for n in range(1, 12):
+        h = ib.Poseidon.new_circom(n)
+        for ins in ([b""] * n, [b"\x01" * 32] * (n - 1) + [b""]):
+            for fn in (h.hash_bytes_be, h.hash_bytes_le):
+                with pytest.raises(ib.PoseidonError) as e:
+                    fn(ins)
+                assert e.value.kind == "EmptyInput"
+
+
+def test_input_length_and_width_errors(ib):
+    h = ib.Poseidon.new_circom(2)
+    for bad in (b"\x01" * 33, b"\x01" * 31, b"\x01"):
+        with pytest.raises(ib.PoseidonError) as e:
+            h.hash_bytes_be([bad, b"\x01" * 32])
+        assert e.value.kind == "InvalidInputLength"
+    with pytest.raises(ib.PoseidonError) as e:
+        h.hash([1])
+    assert e.value.kind == "InvalidNumberOfInputs"
+    with pytest.raises(ib.PoseidonError) as e:
+        h.hash_bytes_be([b"\x01" * 32])
+    assert e.value.kind == "InvalidNumberOfInputs"
+    for n in (0, 13, 14):
+        with pytest.raises(ib.PoseidonError) as e:
+            ib.Poseidon.new_circom(n)
+        assert e.value.kind == "InvalidWidthCircom"
+
+
+def test_circomlibjs_compat_1_to_12_inputs(ib, golden):
+    one, two = be(1), be(2)
+    for n in range(1, 13):
+        h = ib.Poseidon.new_circom(n)
+        assert h.hash_bytes_be([one] * n) == H(golden["circomlibjs_ones"][n - 1])
+        assert h.hash_bytes_be([two] * n) != H(golden["circomlibjs_ones"][n - 1])
+
+
+# ---- pallet/src/poll/zeroes.rs ------------------------------------------------------
+@pytest.mark.parametrize("arity,key", [(2, "binary_zeroes"), (5, "quinary_zeroes")])
+def test_zero_tables(ib, golden, arity, key):
+    table = [H(x) for x in golden[key]]
+    assert ib.get_merkle_zeroes(arity) == table
+    # one batch call re-derives all 32 links of the chain
+    ins = b"".join(z * arity for z in table[:32])
+    out = ib.Poseidon.new_circom(arity).hash_batch(ins)
+    assert [out[i].tobytes() for i in range(32)] == table[1:]
+    assert ib.get_merkle_zeroes(7) == ib.get_merkle_zeroes(5)
+    assert ib.empty_ballot_roots() == [H(x) for x in golden["empty_ballot_roots"]]
+
+
+# ---- pallet/src/tests/extrinsics.rs ---------------------------------------------------
+def _registration_leaves(ib, golden):
+    blk = golden["merge_registration_state_success"]["registration_block"]
+    h4 = ib.Poseidon.new_circom(4)
+    return [h4.hash_bytes_be([H(p["x"]), H(p["y"]), be(1), be(blk)]) for p in golden["participants"]]
+
+
+def test_merge_registration_state_success(ib, golden):
+    g = golden["merge_registration_state_success"]
+    t = ib.new_registration_tree(golden["poll_config"]["registration_depth"])
+    for leaf in _registration_leaves(ib, golden):
+        t.insert(leaf)
+    t, commitment = ib.merge_registrations(t)
+    assert t.root == H(g["registrations_root"])
+    assert commitment == H(g["process_commitment"])
+    assert t.hashes == []
+
+
+def test_merge_interaction_state_success(ib, golden):
+    g = golden["merge_interaction_state_success"]
+    cfg = golden["poll_config"]
+    p = golden["participant"]
+    h5, h4 = ib.Poseidon.new_circom(5), ib.Poseidon.new_circom(4)
+    msg = [H(x) for x in p["message"]]
+    leaf = h4.hash_bytes_be([h5.hash_bytes_be(msg[:5]), h5.hash_bytes_be(msg[5:]),
+                             H(p["shared_pk"]["x"]), H(p["shared_pk"]["y"])])
+    t = ib.new_interaction_tree(cfg["interaction_depth"]).insert(leaf)
+    t, ep, et = ib.merge_interactions(t, 3, cfg["process_subtree_depth"], cfg["tally_subtree_depth"])
+    assert t.root == H(g["interactions_root"])
+    assert (ep, et) == (g["expected_process"], g["expected_tally"])
+
+
+def test_process_messages_public_signals(ib, golden):
+    g = golden["process_messages_public_signals"]
+    t = ib.new_registration_tree(golden["poll_config"]["registration_depth"])
+    for leaf in _registration_leaves(ib, golden):
+        t.insert(leaf)
+    t, commitment = ib.merge_registrations(t)
+    assert t.count + 1 == g["registrations_count_plus_one"]
+    assert t.depth == g["registrations_depth"]
+    assert commitment == H(g["process_commitment"])
+    pk = golden["coordinator_pk"]
+    hsh = ib.Poseidon.new_circom(2).hash([int(pk["x"], 16), int(pk["y"], 16)])
+    assert str(hsh) == g["coord_pub_key_hash_decimal"]
+
+
+def test_participant_limit_reached_quirk(ib):
+    # extrinsics.rs:301-316: depth-2 tree, blank + 3 leaves is completed by insert
+    t = ib.new_registration_tree(2)
+    for i in range(3):
+        t.insert(be(100 + i))
+    assert t.root is not None and t.hashes == []
+    o = O.new_registration_tree(2)
+    for i in range(3):
+        o.insert(be(100 + i))
+    assert t.root == o.root and t.depth == o.depth
+    with pytest.raises(ib.MerkleTreeError) as e:
+        t.merge(False)
+    assert e.value.code == 2
+    with pytest.raises(ib.MerkleTreeError) as e:
+        t.insert(be(7))
+    assert e.value.code == 1
+
+
+# ---- oracle parity, every width, edge values ---------------------------------------------
+@pytest.mark.parametrize("n_inputs", range(1, 13))
+def test_hash_batch_vs_oracle_all_widths(ib, n_inputs):
+    rng = random.Random(300 + n_inputs)
+    rows = [[v] * n_inputs for v in EDGE_VALUES]
+    rows += [[rng.choice(EDGE_VALUES) for _ in range(n_inputs)] for _ in range(40)]
+    rows += [[rng.randrange(1 << 256) for _ in range(n_inputs)] for _ in range(200)]
+    raw = b"".join(be(x) for r in rows for x in r)
+    got = ib.Poseidon.new_circom(n_inputs).hash_batch(raw)
+    exp = c_oracle.hash_batch(n_inputs, raw)
+    assert (got == exp).all()
+    # little-endian wire order
+    raw_le = b"".join(x.to_bytes(32, "little") for r in rows for x in r)
+    got_le = ib.Poseidon.new_circom(n_inputs).hash_batch(raw_le, little_endian=True)
+    assert (got_le[:, ::-1] == exp).all()
+    # x and x + p hash alike whenever x + p still fits 256 bits
+    shifted = b"".join(be(x + P if x + P < (1 << 256) else x) for r in rows for x in r)
+    assert (ib.Poseidon.new_circom(n_inputs).hash_batch(shifted) == exp).all()
+
+
+@pytest.mark.parametrize("n_inputs", [1, 2, 3, 4, 5, 7])
+def test_optimised_kernel_equals_dense_kernel_on_device(ib, n_inputs):
+    """Two device implementations that share no tables: sparse/lazy vs the
+    reference schedule taken literally."""
+    raw = random_fr_bytes(4096 * n_inputs, seed=n_inputs, canonical=False)
+    h = ib.Poseidon.new_circom(n_inputs)
+    assert (h.hash_batch(raw) == h.hash_batch(raw, dense=True)).all()
+
+
+def test_hash2_2_20_pairs_bit_exact_vs_oracle(ib):
+    """BASELINE config 2 at an oracle-affordable size: every output compared."""
+    n = 1 << 17
+    raw = random_fr_bytes(2 * n)
+    got = ib.Poseidon.new_circom(2).hash_batch(raw)
+    assert (got == c_oracle.hash_batch(2, raw)).all()
+
+
+def test_hash5_bit_exact_vs_oracle(ib):
+    n = 1 << 15
+    raw = random_fr_bytes(5 * n, seed=5)
+    got = ib.Poseidon.new_circom(5).hash_batch(raw)
+    assert (got == c_oracle.hash_batch(5, raw)).all()
+
+
+# ---- trees -----------------------------------------------------------------------------------
+SIZES = sorted(set(list(range(0, 41)) + [63, 64, 65, 100, 124, 125, 126, 127, 128, 129, 255, 256, 257,
+                                          624, 625, 626, 1000, 1023, 1024, 1025, 3124, 3125, 3126, 5000]))
+
+
+@pytest.mark.parametrize("arity,full_depth,blank,to_depth", [(2, 13, True, False), (5, 6, False, True),
+                                                            (2, 13, False, True), (5, 6, True, False),
+                                                            (2, 13, True, True), (5, 6, False, False)])
+def test_tree_merge_equals_insert_merge(ib, arity, full_depth, blank, to_depth):
+    """gpu_tree(leaves) == oracle new + insert*N + merge, for ragged sizes."""
+    allv = random_fr_bytes(max(SIZES), seed=arity * 10 + full_depth)
+    for n in SIZES:
+        leaves = allv[:n]
+        rc, root, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
+        t = ib.PollStateTree.new(arity, full_depth, (0, ib.get_merkle_zeroes(arity)[0]) if blank else None)
+        t.extend(leaves)
+        t.merge(to_depth)
+        assert rc == 0
+        assert t.root == root, (arity, n)
+        assert (t.depth, t.count) == (depth, count), (arity, n)
+
+
+@pytest.mark.parametrize("arity,full_depth", [(2, 6), (5, 3)])
+def test_tree_capacity_edges(ib, arity, full_depth):
+    cap = arity ** full_depth
+    allv = random_fr_bytes(cap + 1, seed=99)
+    for blank in (False, True):
+        for n in (cap - 2, cap - 1, cap, cap + 1):
+            total = n + (1 if blank else 0)
+            rc, root, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, True, allv[:n])
+            t = ib.PollStateTree.new(arity, full_depth, (0, ib.get_merkle_zeroes(arity)[0]) if blank else None)
+            if total > cap:
+                assert rc == 1
+                with pytest.raises(ib.MerkleTreeError) as e:
+                    t.extend(allv[:n])
+                assert e.value.code == 1
+                continue
+            t.extend(allv[:n])
+            if total == cap:
+                assert rc == 2 and t.root == root and t.depth == depth
+                with pytest.raises(ib.MerkleTreeError) as e:
+                    t.merge(True)
+                assert e.value.code == 2
+            else:
+                t.merge(True)
+                assert rc == 0 and t.root == root and t.depth == depth
+
+
+def test_state_tree_2_16_registrations(ib):
+    """BASELINE config 3 shape at an oracle-affordable size: blank leaf + 2^16
+    registrations, depth field 16, root depth 17."""
+    leaves = random_fr_bytes(1 << 16, seed=3)
+    t = ib.new_registration_tree(20).extend(leaves)
+    t.merge(False)
+    lv = np.concatenate([np.frombuffer(ib.get_merkle_zeroes(2)[0], dtype=np.uint8).reshape(1, 32), leaves])
+    assert t.root == c_oracle.dense_tree_root(2, 17, lv)
+    assert t.depth == 16 and t.count == 1 << 16
+
+
+def test_message_tree_depth_12_padding(ib):
+    """Quinary tree with full_depth 12 over 5^6+17 leaves: six levels of real
+    work, then zero-sibling padding up to depth 12 (merge(true))."""
+    n = 5 ** 6 + 17
+    leaves = random_fr_bytes(n, seed=12)
+    t = ib.new_interaction_tree(12).extend(leaves)
+    t.merge(True)
+    assert t.root == c_oracle.dense_tree_root(5, 12, leaves)
+    rc, root, depth, count = c_oracle.tree_insert_merge(5, 12, False, True, leaves)
+    assert rc == 0 and root == t.root and depth == t.depth == 6
+
+
+def test_full_size_properties_2_24(ib):
+    """At BASELINE's full size the oracle cannot follow; use size-independent
+    properties: (1) a tree over [x]*2^24 must equal 24 chained self-hashes;
+    (2) root(2^24 leaves) == H(root(left half), root(right half))."""
+    n = 1 << 24
+    x = random_fr_bytes(1, seed=24)
+    leaves = np.repeat(x, n, axis=0)
+    t = ib.PollStateTree.new(2, 24).extend(leaves)           # completed by insert: n == 2^24
+    node = x[0].tobytes()
+    for _ in range(24):
+        node = c_oracle.hash_one([node, node])
+    assert t.root == node
+    leaves = random_fr_bytes(n, seed=2424)
+    whole = ib.PollStateTree.new(2, 24).extend(leaves).root
+    left = ib.PollStateTree.new(2, 23).extend(leaves[: n // 2]).root
+    right = ib.PollStateTree.new(2, 23).extend(leaves[n // 2:]).root
+    assert whole == c_oracle.hash_one([left, right])

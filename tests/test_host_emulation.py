@@ -1,0 +1,164 @@
+"""The device arithmetic (fr.cuh / poseidon.cuh), compiled for the host with
+every PTX block replaced by its C body, against Python integers and the oracle.
+This is how the kernel logic is unit-tested where there is no GPU."""
+import ctypes
+import random
+
+import pytest
+
+import __graft_entry__ as entry
+from oracle import poseidon_ref as O
+from tests import opt_model
+from tests.util import EDGE_VALUES
+
+P = O.P
+R = 1 << 256
+RINV = pow(R, -1, P)
+U8 = ctypes.c_uint32 * 8
+
+
+def limbs(x):
+    return U8(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def val(a):
+    return sum(int(a[i]) << (32 * i) for i in range(8))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    entry.build()
+    from infimum_b200 import build as b
+    lib = ctypes.CDLL(b.HOSTEMU)
+    lib.hostemu_overflow_count.restype = ctypes.c_ulonglong
+    return lib
+
+
+def test_mont_mul_ranges(emu):
+    rng = random.Random(11)
+    lim = 2 * P + (1 << 224)
+    cases = [(a % lim, b % lim) for a in EDGE_VALUES for b in EDGE_VALUES]
+    cases += [(rng.randrange(lim), rng.randrange(lim)) for _ in range(3000)]
+    cases += [(rng.randrange(R), rng.randrange(P)) for _ in range(500)]      # raw 256-bit input x constant
+    base = emu.hostemu_overflow_count()
+    for a, b in cases:
+        r = U8()
+        emu.hostemu_mont_mul(limbs(a), limbs(b), r)
+        assert val(r) % P == a * b * RINV % P
+        assert val(r) < 2 * P + 1
+    assert emu.hostemu_overflow_count() == base
+
+
+@pytest.mark.parametrize("n", range(1, 9))
+def test_lazy_dot(emu, n):
+    rng = random.Random(100 + n)
+    lim = 2 * P + (1 << 224)
+    base = emu.hostemu_overflow_count()
+    for it in range(200):
+        A = [rng.randrange(lim) for _ in range(n)]
+        B = [rng.randrange(P) for _ in range(n)]
+        V = rng.randrange(P)
+        if it < 10:                       # worst case for the range analysis
+            A, B, V = [lim - 1] * n, [P - 1] * n, P - 1
+        elif it < 20:                     # all-ones limbs stress the carry chains
+            A = [(0xFFFFFFFF << (32 * (it % 7))) | 0xFFFFFFFF] * n
+        aa = (ctypes.c_uint32 * (8 * n))(*[(x >> (32 * i)) & 0xFFFFFFFF for x in A for i in range(8)])
+        bb = (ctypes.c_uint32 * (8 * n))(*[(x >> (32 * i)) & 0xFFFFFFFF for x in B for i in range(8)])
+        r = U8()
+        assert emu.hostemu_dot(n, aa, bb, limbs(V) if it % 2 == 0 else None, r) == 0
+        exp = (sum(x * y for x, y in zip(A, B)) + (V if it % 2 == 0 else 0)) * RINV % P
+        assert val(r) % P == exp
+        assert val(r) < lim
+    assert emu.hostemu_overflow_count() == base
+
+
+def test_redc_and_range_steps(emu):
+    rng = random.Random(5)
+    for x in EDGE_VALUES + [rng.randrange(R) for _ in range(300)]:
+        r = U8()
+        emu.hostemu_redc(limbs(x), r)
+        assert val(r) % P == x * RINV % P and val(r) <= P
+        y = limbs(x)
+        emu.hostemu_csub2p(y)
+        assert val(y) % P == x % P
+        assert val(y) < max(2 * P + (1 << 224), x - 2 * P + 1)
+        if x < 2 * P:
+            z = limbs(x)
+            emu.hostemu_csub_p_exact(z)
+            assert val(z) == (x - P if x >= P else x)
+
+
+@pytest.mark.parametrize("t", range(2, 9))
+def test_optimised_hash_equals_oracle(emu, t):
+    rng = random.Random(200 + t)
+    base = emu.hostemu_overflow_count()
+    cases = [[1] * (t - 1), [0] * (t - 1), [R - 1] * (t - 1), [P] * (t - 1), [P - 1] * (t - 1)]
+    cases += [[rng.choice(EDGE_VALUES) for _ in range(t - 1)] for _ in range(4)]
+    cases += [[rng.randrange(R) for _ in range(t - 1)] for _ in range(6)]
+    for i, ins in enumerate(cases):
+        tag = None if i % 3 else rng.randrange(R)
+        exp = O.poseidon_permute_hash([x % P for x in ins], (tag or 0) % P)
+        for le, order in ((0, "big"), (1, "little")):
+            buf = b"".join(x.to_bytes(32, order) for x in ins)
+            out = ctypes.create_string_buffer(32)
+            tagb = tag.to_bytes(32, order) if tag is not None else None
+            assert emu.hostemu_hash(t, buf, tagb, out, le) == 0
+            assert int.from_bytes(out.raw, order) == exp
+    assert emu.hostemu_overflow_count() == base
+
+
+@pytest.mark.parametrize("t", range(2, 14))
+def test_library_grain_constants_equal_oracle(emu, t):
+    ark, mds, rf, rp = O.poseidon_parameters(t)
+    n = len(ark) + t * t
+    buf = (ctypes.c_uint32 * (8 * n))()
+    assert emu.hostemu_dense_params(t, buf) == n
+    got = [sum(int(buf[8 * k + i]) << (32 * i) for i in range(8)) for k in range(n)]
+    assert got[: len(ark)] == list(ark)
+    assert got[len(ark):] == [x for row in mds for x in row]
+
+
+@pytest.mark.parametrize("t", range(2, 9))
+def test_library_optimised_tables_equal_python_derivation(emu, t):
+    T = opt_model.derive(t)
+    words = emu.hostemu_opt_table_words(t)
+    buf = (ctypes.c_uint32 * words)()
+    assert emu.hostemu_opt_table(t, buf) == words
+    el = lambda k: sum(int(buf[8 * k + i]) << (32 * i) for i in range(8))
+    rp = T["rp"]
+    mont = lambda x: x * R % P
+    vform = lambda x: x * R * R % P
+    k = 0
+    assert el(k) == R * R % P; k += 1
+    for i in range(t):
+        assert el(k) == vform(T["C"][0][i]); k += 1
+    assert el(k) == mont(T["C"][0][0]); k += 1
+    for i in range(t):
+        for j in range(t):
+            assert el(k) == mont(T["M"][i][j]); k += 1
+    for i in range(t):
+        for j in range(t):
+            assert el(k) == mont(T["PRE"][i][j]); k += 1
+    for r in range(3):
+        for i in range(t):
+            assert el(k) == vform(T["C"][r + 1][i]); k += 1
+    assert el(k) == vform(T["k"][0]); k += 1
+    for i in range(1, t):
+        assert el(k) == 0; k += 1
+    for j in range(rp):
+        row0, w = T["sparse"][j]
+        for i in range(t):
+            assert el(k) == mont(row0[i]); k += 1
+        for i in range(t - 1):
+            assert el(k) == mont(w[i]); k += 1
+        assert el(k) == vform(T["k"][j + 1] if j + 1 < rp else T["D"][0]); k += 1
+    for i in range(1, t):
+        assert el(k) == mont(T["D"][i]); k += 1
+    for r in range(3):
+        for i in range(t):
+            assert el(k) == vform(T["C"][4 + rp + r + 1][i]); k += 1
+    for j in range(t):
+        assert el(k) == T["M"][0][j]; k += 1
+    for j in range(t):
+        assert el(k) == mont(T["M"][0][j]); k += 1
+    assert k * 8 == words

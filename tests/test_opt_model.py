@@ -1,0 +1,19 @@
+"""The optimised schedule (sparse partial rounds, compressed constants) is an
+exact rewriting of the reference algorithm: model == dense oracle."""
+import random
+
+import pytest
+
+from oracle import poseidon_ref as O
+from tests import opt_model
+
+
+@pytest.mark.parametrize("t", list(range(2, 14)))
+def test_optimised_schedule_equals_dense(t):
+    rng = random.Random(1000 + t)
+    tables = opt_model.derive(t)
+    cases = [[1] * (t - 1), [0] * (t - 1), [O.P - 1] * (t - 1)]
+    cases += [[rng.randrange(O.P) for _ in range(t - 1)] for _ in range(3)]
+    for ins in cases:
+        for tag in (0, 5):
+            assert opt_model.hash_opt(ins, tag, tables) == O.poseidon_permute_hash(ins, tag)
