@@ -1,0 +1,424 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: Poseidon-BN254 hashing and poll-tree merge.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of batch Poseidon
+hash2 (t=3) over 2^24 random Fr pairs per GPU (BASELINE.json configs[1]) with
+the inputs already resident in HBM; hash batches are independent, so ranks
+shard by replication of the unit of work (weak scaling, no collective).  The
+same line also carries, measured in the same process:
+
+  e2e          the same metric through the public host-buffer API
+               (infimum_b200.Poseidon.hash_batch -> inf_poseidon_hash_batch),
+               pinned host input -> device -> pinned host output every step
+  tree_merge   the 2^24-leaf binary poll-tree merge (16 777 215 hash2), device
+               timed, leaves sharded over the N GPUs as contiguous subtrees with
+               ONE all-gather (NCCL) of subtree roots and the top finished on
+               every rank (strong scaling; BASELINE.json's second metric)
+  roofline     integer-multiply roofline of the hash kernel (north star)
+  cpu_baseline the C oracle ("port" of the Rust path) on the host cores, N=1
+
+--impl reference times the CPU restatement of the reference's own path
+(oracle/poseidon_oracle.c; the Rust crate cannot be built here) on the same
+workload, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LOG_PAIRS = 24                      # 2^24 hash2 per GPU per step
+LOG_LEAVES = 24                     # 2^24-leaf poll tree
+W_HASH2 = 218592                    # IMAD-equivalents per hash2 of the reference algorithm
+IMAD_PER_CLK_PER_SM = 64            # CUDA programming guide, 32-bit integer multiply-add, cc 10.0
+METRIC = "Poseidon-BN254 hashes/s"
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active," \
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], None, [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs: uniform field elements, canonical 32-byte big-endian, made on the device
+# ----------------------------------------------------------------------------------------
+def device_random_fr(n, device, seed):
+    """(n, 32) uint8 on `device`: random bytes with the top byte drawn below
+    0x30, i.e. uniform over [0, 0x30<<248) which is 99.2 % of [0, p) and always
+    canonical.  Generated in 2^20-element blocks seeded by block index so that a
+    rank's slice does not depend on the world size."""
+    import torch
+    out = torch.empty((n, 32), dtype=torch.uint8, device=device)
+    blk = 1 << 20
+    g = torch.Generator(device=device)
+    for b0 in range(0, n, blk):
+        g.manual_seed(seed * 1000003 + b0 // blk)
+        m = min(blk, n - b0)
+        x = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=device, generator=g)
+        x[:, 0] = x[:, 0] % 0x30
+        out[b0:b0 + m] = x
+    return out
+
+
+def device_random_fr_range(lo, hi, device, seed):
+    """Rows [lo, hi) of the global array device_random_fr(*, seed) would produce."""
+    import torch
+    blk = 1 << 20
+    parts = []
+    g = torch.Generator(device=device)
+    b = (lo // blk) * blk
+    while b < hi:
+        g.manual_seed(seed * 1000003 + b // blk)
+        x = torch.randint(0, 256, (blk, 32), dtype=torch.uint8, device=device, generator=g)
+        x[:, 0] = x[:, 0] % 0x30
+        parts.append(x[max(lo - b, 0): min(hi - b, blk)])
+        b += blk
+    return torch.cat(parts, dim=0) if parts else torch.empty((0, 32), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline (the oracle "port"), bounded sample
+# ----------------------------------------------------------------------------------------
+def cpu_baseline_hash2(target_seconds=12.0, native=True):
+    import numpy as np
+    from oracle import c_oracle
+    if native:
+        try:   # rebuild with -march=native for the cores of THIS box
+            so = os.path.join(ROOT, "oracle", "liboracle_native.so")
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "NATIVE=1", "OUT=liboracle_native.so",
+                            "PY=" + sys.executable], check=True, capture_output=True)
+            c_oracle.SO = so
+            c_oracle._lib = None
+        except Exception:
+            pass
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0x494E46)
+    probe_n = 1 << 12
+    data = rng.integers(0, 256, size=probe_n * 64, dtype=np.uint8)
+    data[::32] %= 0x30
+    t0 = time.perf_counter()
+    c_oracle.hash_batch(2, data, threads=cores)
+    rate = probe_n / (time.perf_counter() - t0)
+    n = max(1 << 12, min(1 << 22, int(rate * target_seconds)))
+    data = rng.integers(0, 256, size=n * 64, dtype=np.uint8)
+    data[::32] %= 0x30
+    t0 = time.perf_counter()
+    c_oracle.hash_batch(2, data, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "hashes/s", "cores": cores, "kind": "port",
+            "sample": "%d hash2 of the 2^24-pair workload, oracle/poseidon_oracle.c (4x u64 Montgomery, hoisted "
+                      "parameters), %d threads, %.1f s" % (n, cores, dt)}, n, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference's own path on the
+    host cores (the Rust crate cannot be built in this image)."""
+    if rank != 0:
+        return 0
+    per_step = 6.0 if args.steps <= 5 else max(1.0, 60.0 / args.steps)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_hash2(0.5)
+    vals, total_n, total_t = [], 0, 0.0
+    base = None
+    for _ in range(args.steps):
+        base, n, dt = cpu_baseline_hash2(per_step)
+        total_n += n
+        total_t += dt
+    value = total_n / total_t
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "hashes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Fr)",
+            "data": "synthetic", "config": {"workload": "batch Poseidon hash2 (t=3) over 2^24 random Fr pairs; "
+                                                        "bounded sample per step on the host cores"},
+            "cpu_baseline": base, "gpu_launches": 0,
+            "e2e": {"value": value, "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# ours
+# ----------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import infimum_b200 as ib
+    from infimum_b200 import sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = ib.get_context(local_rank)
+    K, Wm = args.steps, args.warmup
+    n = 1 << args.log_pairs
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident step: hash2 over 2^24 pairs ------------------------------------
+    d_in = device_random_fr(2 * n, dev, seed=0x494E46494D554D % (1 << 31) + rank)
+    d_out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    h2 = ib.Poseidon.new_circom(2, ctx)
+    launches = 0
+    with torch.cuda.stream(stream):
+        for _ in range(max(Wm, 3)):
+            h2.hash_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(K):
+            h2.hash_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+            launches += 1
+            ev[i + 1].record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n * K / (total_ms_max * 1e-3)
+
+    # spot check of the timed output against the oracle (rank 0, 64 hashes)
+    ok = None
+    if rank == 0:
+        from oracle import c_oracle
+        idx = torch.arange(0, n, n // 64, device=dev)[:64]
+        pairs = d_in.view(n, 64)[idx].cpu().numpy()
+        ok = bool((d_out[idx].cpu().numpy() == c_oracle.hash_batch(2, pairs, threads=2)).all())
+
+    # ---- end-to-end through the host-buffer API -------------------------------------------
+    e2e_steps = max(1, min(K, 5))
+    h_in = torch.empty((2 * n, 32), dtype=torch.uint8).pin_memory()
+    h_in.copy_(d_in)
+    h_out = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    h_out_np = h_out.numpy()
+    barrier()
+    h2.hash_batch(h_in.numpy(), n, out=h_out_np)       # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h2.hash_batch(h_in.numpy(), n, out=h_out_np)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+    e2e_ok = bool((h_out_np[:: n // 64][:64].copy() == d_out[:: n // 64][:64].cpu().numpy()).all())
+    del h_in, h_out
+
+    # ---- tree merge of the 2^24-leaf poll tree, sharded over the ranks ----------------------
+    n_leaves = 1 << args.log_leaves
+    plan = sharded.make_plan(2, args.log_leaves, n_leaves, prepend_blank_leaf=False, to_depth=True, world=world)
+    lo, hi = plan.leaf_range(rank)
+    del d_in
+    leaves = device_random_fr_range(lo, hi, dev, seed=77)
+    backend = sharded.GpuBackend(ctx)
+    tree_ms, root = [], None
+    for it in range(2 + 3):
+        barrier()
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            root = sharded.sharded_tree_merge(leaves, plan, backend)
+            e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= 2:
+            tree_ms.append(float(t.item()))
+    tree_best = min(tree_ms)
+    n_tree_hashes = n_leaves - 1
+    root_hex = bytes(root.cpu().numpy().tobytes()).hex()
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (hash_batch_kernel<t=3>) ------------------------------
+    props = torch.cuda.get_device_properties(dev)
+    sms = props.multi_processor_count
+    sm_max_mhz = clocks.get("sm_max_mhz") or 1965.0
+    peak = sms * IMAD_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12          # T IMAD/s at the max SM clock
+    avg_launch_ms = statistics.mean(per_launch_ms)
+    achieved = n * W_HASH2 / (avg_launch_ms * 1e-3) / 1e12
+    meas = {}
+    for kind, name in ((0, "imad"), (1, "imad_wide_x2"), (2, "imad_wide_carry_chain_x2")):
+        v, clk = C.c_double(), C.c_double()
+        ctx.check(ctx.lib.inf_measure_imad_peak(ctx.handle, kind, C.byref(v), C.byref(clk)))
+        meas[name] = v.value / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = 6650.0
+    hbm_src = "fallback"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"])
+            hbm_src = "measured"
+        except Exception:
+            pass
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "r01_hash2_traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    gbs = n * 96 / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "imad", "achieved": achieved, "peak": peak, "unit": "TIMAD/s", "frac": achieved / peak,
+        "traffic": traffic,
+        "kernel": "hash_batch_kernel<t=3> (one launch per step)",
+        "work_per_launch": "2^%d hash2 x W=%d IMAD-eq (reference algorithm: 828 field mults x 264)" % (args.log_pairs, W_HASH2),
+        "peak_source": "theoretical: %d SMs x 64 IMAD/clk x %.0f MHz (BASELINE.md 2)" % (sms, sm_max_mhz),
+        "peak_measured": meas, "frac_of_measured_imad": achieved / meas["imad"] if meas.get("imad") else None,
+        "avg_launch_ms": avg_launch_ms,
+        "note": "frac is reference-equivalent work: the kernel runs the sparse/lazy schedule (594 field mults, "
+                "~68k IMAD-pipe instructions per hash2), so frac may exceed 1; executed pipe utilisation is in profiles/",
+        "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "bytes_per_hash": 96},
+    }
+    base, _, _ = cpu_baseline_hash2(12.0) if world == 1 and not args.no_cpu_baseline else (None, 0, 0)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "hashes/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8 (254-bit Fr, Montgomery)", "data": "synthetic",
+        "config": {"workload": "batch Poseidon hash2 (t=3, circom parameters) over 2^%d random Fr pairs per GPU, "
+                               "bit-exact vs oracle" % args.log_pairs,
+                   "pairs_per_gpu": n, "input_bytes_per_step": n * 64, "output_bytes_per_step": n * 32,
+                   "l2": "inputs (1 GiB) larger than L2 (126 MB); no flush needed",
+                   "parallelism": "replicas x%d, no collective" % world},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "hashes/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 32,
+                "steps": e2e_steps, "api": "infimum_b200.Poseidon.hash_batch -> inf_poseidon_hash_batch (pinned host buffers)",
+                "matches_device_run": e2e_ok},
+        "roofline": roofline,
+        "tree_merge": {"leaves": n_leaves, "hashes": n_tree_hashes, "ms": tree_best, "ms_all": tree_ms,
+                       "hashes_per_s": n_tree_hashes / (tree_best * 1e-3), "n_gpus": world, "scaling": "strong",
+                       "shard_level": plan.level, "subtrees": plan.n_subtrees,
+                       "collective": "one all_gather of <=%d x 32 B subtree roots per rank (NCCL)" %
+                                     max(e - b for b, e in plan.subtree_ranges) if world > 1 else "none (1 GPU)",
+                       "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / peak,
+                       "root": root_hex},
+        "bit_exact_sample": ok,
+    }
+    if base:
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-pairs", type=int, default=LOG_PAIRS)
+    ap.add_argument("--log-leaves", type=int, default=LOG_LEAVES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    world = _env_int("WORLD_SIZE", 1)
+    rank = _env_int("RANK", 0)
+    local_rank = _env_int("LOCAL_RANK", 0)
+    if args.gpus > 1 and world == 1 and args.impl == "ours":
+        # convenience: relaunch under torchrun when called directly
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] \
+            + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    rc = run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -145,14 +145,17 @@ int inf_tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pr
                        int to_depth, const void* d_leaves, uint64_t n_leaves, uint8_t root[32],
                        uint32_t* insert_depth, uint32_t* root_depth, int* has_root, void* stream);
 
-/* Building block for sharded trees: reduce `n_in` consecutive nodes of level
+/* Building block for sharded trees: reduce a run of consecutive nodes of level
  * `level_in` (device memory) by `n_levels` levels, padding the right edge of
- * level l with zeroes[l].  Writes ceil(n_in / arity^n_levels) nodes to d_out
- * (device) and that count to *n_out.  Enqueued on `stream`; does not
- * synchronise.  d_out may alias nothing; scratch is owned by the context. */
+ * level l with zeroes[l].  The run is `shift` copies of zeroes[level_in]
+ * followed by the n_in nodes at d_in (shift = 1 on the rank that owns leaf 0 of
+ * a registration tree — the blank state leaf, state.rs:48-52 — else 0).
+ * Writes ceil((shift + n_in) / arity^n_levels) nodes to d_out (device) and that
+ * count to *n_out.  Enqueued on `stream`; does not synchronise.  Scratch is
+ * owned by the context. */
 int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,
-                        const void* d_in, uint64_t n_in, void* d_out, uint64_t* n_out,
-                        void* stream);
+                        uint64_t shift, const void* d_in, uint64_t n_in, void* d_out,
+                        uint64_t* n_out, void* stream);
 
 /* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
  * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */

@@ -87,7 +87,8 @@ def load() -> C.CDLL:
     lib.inf_tree_merge_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint64, vp, u32p,
                                        u32p, ip, vp]
     lib.inf_tree_merge_dev.restype = C.c_int
-    lib.inf_tree_reduce_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, u64p, vp]
+    lib.inf_tree_reduce_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp,
+                                        u64p, vp]
     lib.inf_tree_reduce_dev.restype = C.c_int
     lib.inf_merge_registrations.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, u32p]
     lib.inf_merge_registrations.restype = C.c_int

@@ -408,8 +408,8 @@ int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepen
 }
 
 int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,
-                        const void* d_in, uint64_t n_in, void* d_out, uint64_t* n_out,
-                        void* stream) {
+                        uint64_t shift, const void* d_in, uint64_t n_in, void* d_out,
+                        uint64_t* n_out, void* stream) {
     if (!ctx || !d_out) return INF_ERR_NULL_POINTER;
     if (n_in && !d_in) return INF_ERR_NULL_POINTER;
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
@@ -417,28 +417,32 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
     Bind bind(ctx);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
-    if (n_levels == 0) {
-        if (n_in) CU(cudaMemcpyAsync(d_out, d_in, (size_t)n_in * 32, cudaMemcpyDeviceToDevice, st));
-        if (n_out) *n_out = n_in;
-        return INF_OK;
-    }
-    if (n_in == 0) {
+    const uint64_t n_total = n_in + shift;
+    if (n_total == 0) {
         if (n_out) *n_out = 0;
         return INF_OK;
     }
-    const uint64_t n1 = (n_in + arity - 1) / arity;
+    if (n_levels == 0) {
+        for (uint64_t i = 0; i < shift; i++)
+            CU(cudaMemcpyAsync((char*)d_out + 32 * i, Z[level_in], 32, cudaMemcpyHostToDevice, st));
+        if (n_in) CU(cudaMemcpyAsync((char*)d_out + 32 * shift, d_in, (size_t)n_in * 32, cudaMemcpyDeviceToDevice, st));
+        if (n_out) *n_out = n_total;
+        return INF_OK;
+    }
+    const uint64_t n1 = (n_total + arity - 1) / arity;
     const uint64_t n2 = (n1 + arity - 1) / arity;
     int rc;
     if (n_levels > 1 && (rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
     if (n_levels > 2 && (rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
     const void* cur = d_in;
-    uint64_t n_cur = n_in;
+    uint64_t n_cur = n_in, sh = shift;
     for (uint32_t l = 0; l < n_levels; l++) {
-        const uint64_t n_next = (n_cur + arity - 1) / arity;
+        const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
         void* dst = (l + 1 == n_levels) ? d_out : ctx->scratch[l & 1];
-        CU(launch_level(arity, cur, 0, n_cur, dst, n_next, Z[level_in + l], st));
+        CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[level_in + l], st));
         cur = dst;
         n_cur = n_next;
+        sh = 0;
     }
     if (n_out) *n_out = n_cur;
     return INF_OK;

@@ -63,6 +63,75 @@ __global__ void __launch_bounds__(256) imad_wide_kernel(uint32_t* sink, uint32_t
     if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+// kind 2: the carry-chain shape the field arithmetic actually uses — chains of
+// four IMAD.WIDE.U32 linked by the carry predicate (mad.lo.cc / madc.hi.cc
+// pairs), four independent chains per thread.  Counted as 2 IMAD-eq per wide.
+__global__ void __launch_bounds__(256) imad_chain_kernel(uint32_t* sink, uint32_t a, uint32_t b,
+                                                          long long* cycles) {
+    uint32_t r[4][9], m[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) r[c][k] = threadIdx.x + k + c;
+#pragma unroll
+        for (int k = 0; k < 4; k++) m[c][k] = a + k * 77 + c;
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                asm volatile(
+                    "mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+                    "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+                    "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+                    "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+                    "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+                    "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+                    "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+                    "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+                    "addc.u32        %8, %8, 0;"
+                    : "+r"(r[c][0]), "+r"(r[c][1]), "+r"(r[c][2]), "+r"(r[c][3]), "+r"(r[c][4]),
+                      "+r"(r[c][5]), "+r"(r[c][6]), "+r"(r[c][7]), "+r"(r[c][8])
+                    : "r"(m[c][0]), "r"(m[c][1]), "r"(m[c][2]), "r"(m[c][3]), "r"(b));
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc ^= r[c][k];
+    if (acc == 0x12345u) sink[0] = acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// kind 3: mad.hi.u32 alone (IMAD.HI), 8 independent chains.
+__global__ void __launch_bounds__(256) imad_hi_kernel(uint32_t* sink, uint32_t a, uint32_t b,
+                                                       long long* cycles) {
+    uint32_t x[CHAINS];
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) x[k] = threadIdx.x * 0x01010101u + k;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < CHAINS; k++)
+                asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) acc ^= x[k];
+    if (acc == 0x12345u) sink[0] = acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 }  // namespace
 
 cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double* clock_mhz,
@@ -81,7 +150,9 @@ cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double*
     for (int rep = 0; rep < 5 && e == cudaSuccess; rep++) {
         cudaEventRecord(e0, st);
         if (kind == 0) imad_lo_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
-        else imad_wide_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else if (kind == 1) imad_wide_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else if (kind == 2) imad_chain_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else imad_hi_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
         cudaEventRecord(e1, st);
         e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) break;
@@ -98,10 +169,12 @@ cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double*
     cudaFree(sink);
     cudaFree(cyc);
     if (e != cudaSuccess) return e;
-    const double ops = (double)blocks * threads * (double)ITERS * 4 * CHAINS * (kind == 0 ? 1.0 : 2.0);
+    // instructions per thread per iteration: 32 everywhere (4 x 8 chains, or 2 x 4 chains x 4 wide)
+    const double ops = (double)blocks * threads * (double)ITERS * 32 * ((kind == 1 || kind == 2) ? 2.0 : 1.0);
     *imad_per_s = ops / (best_ms * 1e-3);
-    // one block's clock64 span vs. wall time of the whole grid (8 blocks per SM
-    // run concurrently, 2048 threads), so this is the SM clock under this load
+    // SM cycles one resident block spent in the loop over the wall time of the
+    // launch: the SM clock under this load, to first order (the grid is exactly
+    // one wave of 8 x 256 threads per SM)
     *clock_mhz = best_cycles > 0 ? (double)best_cycles / (best_ms * 1e-3) / 1e6 : 0.0;
     return cudaSuccess;
 }

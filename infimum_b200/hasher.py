@@ -94,9 +94,10 @@ class Poseidon:
         return self.domain_tag.to_bytes(32, "little" if flags & _lib.FLAG_LITTLE_ENDIAN else "big")
 
     def hash_batch(self, inputs, n: Optional[int] = None, little_endian: bool = False,
-                   dense: bool = False) -> np.ndarray:
+                   dense: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
         """n independent hashes.  `inputs`: bytes / uint8 array of n*(width-1)*32
-        bytes (host memory).  Returns an (n, 32) uint8 array."""
+        bytes (host memory; pinned memory makes the copies faster).  Returns an
+        (n, 32) uint8 array (`out` if given, e.g. a pinned buffer)."""
         a = _as_u8(inputs)
         k = self.width - 1
         if n is None:
@@ -105,12 +106,15 @@ class Poseidon:
             n = a.size // (k * 32)
         if a.size != n * k * 32:
             raise PoseidonError("InvalidInputLength", len=a.size, modulus_bytes_len=HASH_LEN)
-        out = np.empty((n, 32), dtype=np.uint8)
+        if out is None:
+            out = np.empty((n, 32), dtype=np.uint8)
+        elif out.dtype != np.uint8 or out.size != n * 32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous uint8 array of n*32 bytes")
         flags = _lib.FLAG_LITTLE_ENDIAN if little_endian else 0
         fn = self.ctx.lib.inf_poseidon_hash_batch_dense if dense else self.ctx.lib.inf_poseidon_hash_batch
         rc = fn(self.ctx.handle, k, flags, self._tag_bytes(flags), a.ctypes.data, n, out.ctypes.data)
         self.ctx.check(rc)
-        return out
+        return out.reshape(n, 32)
 
     def hash_batch_device(self, d_in: int, n: int, d_out: int, stream: int = 0, little_endian: bool = False):
         """Same on device pointers (ints); enqueued on `stream` (a cudaStream_t

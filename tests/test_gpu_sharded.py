@@ -1,0 +1,73 @@
+"""Sharded tree merge on the GPU data plane (GpuBackend over inf_tree_reduce_dev)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from tests.util import random_fr_bytes
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(2, 20, 100000, True, False), (2, 17, 1 << 17, False, True), (2, 21, (1 << 16) + 1, True, False),
+         (5, 9, 200000, False, True), (5, 7, 5 ** 7 - 3, False, True), (2, 12, 3, True, False), (5, 4, 1, False, True)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_emulated_world_on_one_gpu(world):
+    from infimum_b200 import sharded
+    backend = sharded.GpuBackend(device=0)
+    for arity, full_depth, n, blank, to_depth in CASES:
+        leaves = random_fr_bytes(n, seed=n % 1000 + arity)
+        plan = sharded.make_plan(arity, full_depth, n, blank, to_depth, world)
+        root = sharded.emulated_sharded_merge(torch.from_numpy(leaves).cuda(), plan, backend)
+        rc, exp, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
+        assert rc == 0 and root.cpu().numpy().tobytes() == exp, (arity, n, world)
+        assert plan.insert_depth == depth
+
+
+WORKER = r"""
+import os, sys, json
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["INF_ROOT"])
+from infimum_b200 import sharded
+from tests.util import random_fr_bytes
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+backend = sharded.GpuBackend(device=rank)
+out = []
+for arity, full_depth, n, blank, to_depth in json.loads(os.environ["INF_CASES"]):
+    plan = sharded.make_plan(arity, full_depth, n, blank, to_depth, world)
+    leaves = random_fr_bytes(n, seed=n % 1000 + arity)
+    lo, hi = plan.leaf_range(rank)
+    root = sharded.sharded_tree_merge(torch.from_numpy(leaves[lo:hi].copy()).cuda(), plan, backend)
+    out.append(root.cpu().numpy().tobytes().hex())
+if rank == 0:
+    print("ROOTS " + json.dumps(out))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_nccl_two_ranks(tmp_path):
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, INF_ROOT=root, INF_CASES=json.dumps(CASES))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("ROOTS ")][0]
+    roots = json.loads(line[6:])
+    for (arity, full_depth, n, blank, to_depth), got in zip(CASES, roots):
+        leaves = random_fr_bytes(n, seed=n % 1000 + arity)
+        rc, exp, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
+        assert got == exp.hex()

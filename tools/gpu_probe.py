@@ -15,7 +15,7 @@ from tests.util import random_fr_bytes  # noqa: E402
 
 out = {}
 ctx = ib.get_context(0)
-for kind, name in ((0, "imad_lo"), (1, "imad_wide_x2")):
+for kind, name in ((0, "imad_lo"), (1, "imad_wide_x2"), (2, "imad_wide_carry_chain_x2"), (3, "imad_hi")):
     v, clk = C.c_double(), C.c_double()
     ctx.check(ctx.lib.inf_measure_imad_peak(ctx.handle, kind, C.byref(v), C.byref(clk)))
     out[name] = {"imad_per_s": v.value, "clock_mhz": clk.value}
@@ -30,7 +30,9 @@ for k, logn in ((2, 20), (2, 22), (2, 24), (5, 20), (5, 22), (4, 20), (3, 20)):
     d_in = src.repeat(reps, 1)[: n * k].contiguous()
     d_out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     h = ib.Poseidon.new_circom(k, ctx)
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     for _ in range(2):
         h.hash_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), st)
     torch.cuda.synchronize()
