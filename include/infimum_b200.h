@@ -16,8 +16,10 @@
  *   - Calls on one inf_ctx must be serialised by the caller (like `&mut self`,
  *     pallet/src/hash/poseidon.rs:78); distinct contexts are independent.
  *   - Host-buffer calls are synchronous.  `_dev` calls take device pointers,
- *     enqueue on the given CUDA stream (a cudaStream_t passed as void*, NULL =
- *     the context's own stream) and return without synchronising unless noted.
+ *     enqueue on the given CUDA stream (a cudaStream_t passed as void*; NULL =
+ *     the context's own non-blocking stream, so pass cudaStreamLegacy /
+ *     cudaStreamPerThread explicitly to mean a default stream) and return
+ *     without synchronising unless noted.
  *   - There is no CPU fallback: without a usable CUDA device inf_init fails.
  *
  * Return codes (int): 0 ok.

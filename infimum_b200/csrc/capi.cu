@@ -28,6 +28,8 @@ struct inf_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // copy/compute overlap for host-buffer calls
+    cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
     void* scratch[2] = {nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
     void* io[2] = {nullptr, nullptr};          // staging for host-buffer calls
@@ -137,9 +139,14 @@ int check_hash_args(inf_ctx* ctx, uint32_t n_inputs, const void* in, uint64_t n,
 
 // Core of the tree merge on device-resident leaves.  Leaves the root (if any)
 // in host memory.  `st` is synchronised before return.
+// If h_leaves is non-null the leaves are still in host memory and d_leaves is
+// the (uninitialised) device staging area for them: level 0 is then cut into
+// chunks that rotate over the three pipeline streams, each uploading its slice
+// of leaves and hashing it, so the upload hides behind the hashing.
 int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank, int to_depth,
                    const void* d_leaves, uint64_t n_leaves, uint8_t* root, uint32_t* insert_depth,
-                   uint32_t* root_depth, int* has_root, cudaStream_t st) {
+                   uint32_t* root_depth, int* has_root, cudaStream_t st,
+                   const uint8_t* h_leaves = nullptr) {
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (full_depth > 32) return INF_ERR_BAD_DEPTH;
     if (n_leaves && !d_leaves) return INF_ERR_NULL_POINTER;
@@ -171,6 +178,7 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
     if (rdepth == 0) {
         // single node: the blank leaf itself, or the only leaf
         if (blank) memcpy(root_local, Z[0], 32);
+        else if (h_leaves) memcpy(root_local, h_leaves, 32);
         else CU(cudaMemcpyAsync(root_local, d_leaves, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     } else {
@@ -182,7 +190,32 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
         if (rc) return rc;
         const void* cur = d_leaves;
         uint64_t n_cur = n_leaves, sh = shift;
-        for (uint32_t l = 0; l < rdepth; l++) {
+        uint32_t l_first = 0;
+        if (h_leaves) {
+            const uint64_t chunk_out = 1ull << 19;
+            int k = 0;
+            for (uint64_t o0 = 0; o0 < n1; o0 += chunk_out, k++) {
+                const uint64_t o1 = std::min<uint64_t>(o0 + chunk_out, n1);
+                const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
+                const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
+                cudaStream_t ps = ctx->pipe[k % 3];
+                char* dl = (char*)d_leaves + leaf_lo * 32;
+                if (leaf_hi > leaf_lo)
+                    CU(cudaMemcpyAsync(dl, h_leaves + leaf_lo * 32, (leaf_hi - leaf_lo) * 32,
+                                       cudaMemcpyHostToDevice, ps));
+                CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo,
+                                (char*)ctx->scratch[0] + o0 * 32, o1 - o0, Z[0], ps));
+            }
+            for (int i = 0; i < 3; i++) {
+                CU(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
+                CU(cudaStreamWaitEvent(st, ctx->pipe_done[i], 0));
+            }
+            cur = ctx->scratch[0];
+            n_cur = n1;
+            sh = 0;
+            l_first = 1;
+        }
+        for (uint32_t l = l_first; l < rdepth; l++) {
             const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
             void* dst = ctx->scratch[l & 1];
             CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[l], st));
@@ -250,6 +283,12 @@ int inf_init(int device, inf_ctx** out) {
         return fail(cuda_fail(nullptr, e, "cudaDeviceGetAttribute"));
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(cuda_fail(nullptr, e, "cudaStreamCreate"));
+    for (int i = 0; i < 3; i++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking)) != cudaSuccess)
+            return fail(cuda_fail(nullptr, e, "cudaStreamCreate"));
+        if ((e = cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming)) != cudaSuccess)
+            return fail(cuda_fail(nullptr, e, "cudaEventCreate"));
+    }
     try {
         for (int t = 2; t <= 8; t++) {
             std::vector<uint32_t> tbl = host::build_opt_table(t);
@@ -299,6 +338,10 @@ void inf_destroy(inf_ctx* ctx) {
         }
         for (int t = 0; t < 14; t++)
             if (ctx->d_dense[t]) cudaFree(ctx->d_dense[t]);
+        for (int i = 0; i < 3; i++) {
+            if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+            if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+        }
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -314,20 +357,40 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
                           stream ? (cudaStream_t)stream : ctx->stream, false);
 }
 
+// Host-buffer batch: the batch is cut into chunks that rotate over three
+// streams, each doing H2D -> kernel -> D2H for its chunk, so that with pinned
+// host buffers the copies of one chunk hide behind the hashing of another (the
+// path is compute-bound: ~8 ns of hashing per 96 bytes moved).
 static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
                            const uint8_t* in, uint64_t n, uint8_t* out, bool dense) {
     int rc = check_hash_args(ctx, n_inputs, in, n, out);
     if (rc) return rc;
     if (n == 0) return INF_OK;
     Bind bind(ctx);
-    const size_t in_bytes = (size_t)n * n_inputs * 32, out_bytes = (size_t)n * 32;
-    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], in_bytes))) return rc;
-    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], out_bytes))) return rc;
-    CU(cudaMemcpyAsync(ctx->io[0], in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, ctx->io[0], n, ctx->io[1], ctx->stream, dense)))
-        return rc;
-    CU(cudaMemcpyAsync(out, ctx->io[1], out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    const uint64_t super = 1ull << 24;                 // device staging is sized for at most 2^24 hashes
+    const uint64_t chunk = 1ull << 19;
+    const size_t in_row = (size_t)n_inputs * 32;
+    const uint64_t n_stage = std::min<uint64_t>(n, super);
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_stage * in_row))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], n_stage * 32))) return rc;
+    for (uint64_t base = 0; base < n; base += super) {
+        const uint64_t m = std::min<uint64_t>(super, n - base);
+        int k = 0;
+        for (uint64_t off = 0; off < m; off += chunk, k++) {
+            const uint64_t c = std::min<uint64_t>(chunk, m - off);
+            cudaStream_t st = (m <= chunk) ? ctx->stream : ctx->pipe[k % 3];
+            char* d_in = (char*)ctx->io[0] + off * in_row;
+            char* d_out = (char*)ctx->io[1] + off * 32;
+            CU(cudaMemcpyAsync(d_in, in + (base + off) * in_row, c * in_row, cudaMemcpyHostToDevice, st));
+            if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, d_out, st, dense))) return rc;
+            CU(cudaMemcpyAsync(out + (base + off) * 32, d_out, c * 32, cudaMemcpyDeviceToHost, st));
+        }
+        if (m <= chunk) {
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            for (int i = 0; i < 3; i++) CU(cudaStreamSynchronize(ctx->pipe[i]));
+        }
+    }
     return INF_OK;
 }
 
@@ -401,10 +464,9 @@ int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepen
     if (n_leaves) {
         int rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->io[0], leaves, (size_t)n_leaves * 32, cudaMemcpyHostToDevice, ctx->stream));
     }
     return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, ctx->io[0], n_leaves,
-                          root, insert_depth, root_depth, has_root, ctx->stream);
+                          root, insert_depth, root_depth, has_root, ctx->stream, leaves);
 }
 
 int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,

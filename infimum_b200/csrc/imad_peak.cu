@@ -38,21 +38,19 @@ __global__ void __launch_bounds__(256) imad_lo_kernel(uint32_t* sink, uint32_t a
 
 __global__ void __launch_bounds__(256) imad_wide_kernel(uint32_t* sink, uint32_t a, uint32_t b,
                                                          long long* cycles) {
+    // x = lo32(x) * b + x : the multiplicand depends on the accumulator, so the
+    // product cannot be hoisted out of the loop (a loop-invariant mad.wide is
+    // strength-reduced by ptxas into 64-bit adds, which measures the ALU).
     unsigned long long x[CHAINS];
-    uint32_t m[CHAINS];
 #pragma unroll
-    for (int k = 0; k < CHAINS; k++) {
-        x[k] = threadIdx.x + k;
-        m[k] = a + k;
-    }
+    for (int k = 0; k < CHAINS; k++) x[k] = ((unsigned long long)(a + k) << 32) | (threadIdx.x + k);
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
 #pragma unroll
-            for (int k = 0; k < CHAINS; k++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[k]) : "r"(m[k]), "r"(b));
+            for (int k = 0; k < CHAINS; k++) x[k] = (unsigned long long)(uint32_t)x[k] * b + x[k];
         }
     }
     const long long t1 = clock64();

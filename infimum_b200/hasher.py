@@ -118,7 +118,8 @@ class Poseidon:
 
     def hash_batch_device(self, d_in: int, n: int, d_out: int, stream: int = 0, little_endian: bool = False):
         """Same on device pointers (ints); enqueued on `stream` (a cudaStream_t
-        value, 0 = the context's stream); does not synchronise."""
+        value; 0 = the context's own stream, 1 = CUDA's legacy default stream);
+        does not synchronise."""
         flags = _lib.FLAG_LITTLE_ENDIAN if little_endian else 0
         rc = self.ctx.lib.inf_poseidon_hash_batch_dev(self.ctx.handle, self.width - 1, flags,
                                                       self._tag_bytes(flags), d_in, n, d_out, stream or None)

@@ -92,10 +92,13 @@ class GpuBackend:
         if n_out == 0:
             return out
         got = C.c_uint64()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's current stream; its legacy default stream has handle 0, which the
+        # C ABI reads as "the context's own stream", so name it explicitly
+        # (cudaStreamLegacy == 0x1) to stay ordered with the surrounding torch ops
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         rc = self.ctx.lib.inf_tree_reduce_dev(self.ctx.handle, arity, level_in, n_levels, shift,
                                               nodes.data_ptr() if n_in else None, n_in, out.data_ptr(),
-                                              C.byref(got), stream or None)
+                                              C.byref(got), stream)
         self.ctx.check(rc)
         assert got.value == n_out
         return out

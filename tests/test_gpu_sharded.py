@@ -26,7 +26,7 @@ def test_emulated_world_on_one_gpu(world):
         plan = sharded.make_plan(arity, full_depth, n, blank, to_depth, world)
         root = sharded.emulated_sharded_merge(torch.from_numpy(leaves).cuda(), plan, backend)
         rc, exp, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
-        assert rc == 0 and root.cpu().numpy().tobytes() == exp, (arity, n, world)
+        assert rc in (0, 2) and root.cpu().numpy().tobytes() == exp, (arity, n, world)   # rc 2: completed by insert
         assert plan.insert_depth == depth
 
 

@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Range analysis of the device arithmetic (infimum_b200/csrc/fr.cuh, poseidon.cuh).
+
+Values are tracked as multiples of p.  rho = p / 2^256.  A lazy Montgomery
+dot of terms (alpha_j p) x (beta_j p) plus V < p gives a result below
+(rho * sum alpha_j beta_j + 1 + rho) p, and csub2p leaves max(2 + eps, x - 2).
+The script walks the schedule for each width and prints the largest value ever
+held, which must stay below 2^256 / p = 5.29.
+"""
+P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+RHO = P / 2 ** 256
+LIM = 2 ** 256 / P
+EPS = 2 ** 224 / P
+
+
+def dot(terms, v=1.0):
+    return RHO * (sum(a * b for a, b in terms) + v) + 1.0
+
+
+def csub2p(x):
+    return max(2 + EPS, x - 2)
+
+
+def sbox(x, track):
+    x2 = dot([(x, x)], 0); track(x2)
+    x4 = dot([(x2, x2)], 0); track(x4)
+    x5 = dot([(x4, x)], 0); track(x5)
+    return x5
+
+
+def run(t, rp):
+    worst = [0.0]
+
+    def track(x):
+        worst[0] = max(worst[0], x)
+        assert x < LIM, (t, x)
+        return x
+
+    s = [track(dot([(LIM, 1.0)]))] * t                     # absorb: raw 256-bit x R^2 + V
+    for r in range(4):                                       # first half
+        x = [sbox(v, track) for v in s]
+        s = [csub2p(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
+    for j in range(rp):                                      # partial rounds
+        x0 = sbox(s[0], track)
+        n0 = csub2p(track(dot([(x0, 1.0)] + [(si, 1.0) for si in s[1:]])))
+        s = [n0] + [csub2p(track(si + track(dot([(x0, 1.0)], 0)))) for si in s[1:]]
+    s = [s[0]] + [csub2p(track(si + 1.0)) for si in s[1:]]
+    for r in range(3):
+        x = [sbox(v, track) for v in s]
+        s = [csub2p(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
+    x = [sbox(v, track) for v in s]
+    out = track(dot([(xi, 1.0) for xi in x], 0))
+    out = csub2p(out)
+    assert out < 3.0                                          # two exact subtractions of p suffice
+    return worst[0], out
+
+
+if __name__ == "__main__":
+    RP = {2: 56, 3: 57, 4: 56, 5: 60, 6: 60, 7: 63, 8: 64}
+    print("limit 2^256/p = %.4f, rho = p/2^256 = %.4f" % (LIM, RHO))
+    for t in range(2, 9):
+        w, o = run(t, RP[t])
+        print("t=%d: largest intermediate %.3f p, pre-canonical output < %.3f p" % (t, w, o))

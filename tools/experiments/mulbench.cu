@@ -1,0 +1,115 @@
+// A/B microbenchmark: Montgomery multiplication throughput of the two field
+// representations on the device, in the occupancy regime of the real kernels
+// (128-thread blocks, two independent multiplication chains per thread).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I infimum_b200/csrc -I tools/experiments tools/experiments/mulbench.cu -o tools/_bin/mulbench
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "poseidon.cuh"
+#include "fr29.cuh"
+using namespace inf;
+
+constexpr int ITERS = 2000;
+
+__global__ void __launch_bounds__(128, 4) k_mul32(uint32_t* out, const uint32_t* in) {
+    uint32_t x[8], y[8], z[8];
+    for (int k = 0; k < 8; k++) { x[k] = in[k] + threadIdx.x; y[k] = in[8 + k]; z[k] = in[16 + k] ^ threadIdx.x; }
+    x[7] &= 0x1fffffff; y[7] &= 0x1fffffff; z[7] &= 0x1fffffff;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[8], u[8];
+        mont_mul(t, x, y);
+        mont_mul(u, z, y);
+        for (int k = 0; k < 8; k++) { x[k] = t[k]; z[k] = u[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 8; k++) acc ^= x[k] ^ z[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <bool SQR>
+__global__ void __launch_bounds__(128, 4) k_mul29(uint32_t* out, const uint32_t* in) {
+    uint32_t x[9], y[9], z[9];
+    for (int k = 0; k < 9; k++) { x[k] = (in[k] + threadIdx.x) & LMASK; y[k] = in[9 + k] & LMASK; z[k] = (in[18 + k] ^ threadIdx.x) & LMASK; }
+    x[8] &= 0xffffff; y[8] &= 0x3fffff; z[8] &= 0xffffff;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[9], u[9];
+        if (SQR) { sqr29(t, x); sqr29(u, z); }
+        else { mul29(t, x, y); mul29(u, z, y); }
+        for (int k = 0; k < 9; k++) { x[k] = t[k]; z[k] = u[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 9; k++) acc ^= x[k] ^ z[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// 3-term lazy dot (the partial-round shape for t=3) in both representations
+__global__ void __launch_bounds__(128, 4) k_dot32(uint32_t* out, const uint32_t* in) {
+    uint32_t s[3][8], b[24];
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 8; k++) { s[j][k] = in[8 * j + k] + threadIdx.x; b[8 * j + k] = in[32 + 8 * j + k]; }
+    for (int j = 0; j < 3; j++) { s[j][7] &= 0x1fffffff; b[8 * j + 7] &= 0x1fffffff; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[8];
+        dot<3, 8>(t, &s[0][0], b, nullptr);
+        for (int k = 0; k < 8; k++) { s[0][k] = s[1][k]; s[1][k] = s[2][k]; s[2][k] = t[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 8; k++) acc ^= s[0][k] ^ s[1][k] ^ s[2][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void __launch_bounds__(128, 4) k_dot29(uint32_t* out, const uint32_t* in) {
+    uint32_t s[3][9], b[27];
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 9; k++) { s[j][k] = (in[9 * j + k] + threadIdx.x) & LMASK; b[9 * j + k] = in[32 + 9 * j + k] & LMASK; }
+    for (int j = 0; j < 3; j++) { s[j][8] &= 0xffffff; b[9 * j + 8] &= 0x3fffff; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[9];
+        dot29<3, 9>(t, &s[0][0], b, nullptr, nullptr);
+        for (int k = 0; k < 9; k++) { s[0][k] = s[1][k]; s[1][k] = s[2][k]; s[2][k] = t[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 9; k++) acc ^= s[0][k] ^ s[1][k] ^ s[2][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <typename F> float time_it(F f) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) { cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms; }
+    return best;
+}
+
+int main(int argc, char** argv) {
+    const bool profile = argc > 1;
+    uint32_t h[64]; for (int i = 0; i < 64; i++) h[i] = 0x9e3779b9u * (i + 1);
+    uint32_t *in, *out; cudaMalloc(&in, sizeof h); cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (profile) {      // one launch per kernel, for ncu
+        const int blocks = sms * 16, threads = 128;
+        cudaMalloc(&out, (size_t)blocks * threads * 4);
+        k_mul32<<<blocks, threads>>>(out, in);
+        k_mul29<false><<<blocks, threads>>>(out, in);
+        k_mul29<true><<<blocks, threads>>>(out, in);
+        k_dot32<<<blocks, threads>>>(out, in);
+        k_dot29<<<blocks, threads>>>(out, in);
+        cudaDeviceSynchronize();
+        printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    for (int bps : {2, 4, 8}) {
+        const int blocks = sms * bps * 4, threads = 128;   // several waves
+        cudaMalloc(&out, (size_t)blocks * threads * 4);
+        const double n = (double)blocks * threads * ITERS;
+        float ms;
+        ms = time_it([&] { k_mul32<<<blocks, threads>>>(out, in); });        printf("blocks/SM-wave %d: mul32  %8.2f G mul/s\n", bps, 2 * n / ms / 1e6);
+        ms = time_it([&] { k_mul29<false><<<blocks, threads>>>(out, in); }); printf("blocks/SM-wave %d: mul29  %8.2f G mul/s\n", bps, 2 * n / ms / 1e6);
+        ms = time_it([&] { k_mul29<true><<<blocks, threads>>>(out, in); });  printf("blocks/SM-wave %d: sqr29  %8.2f G sqr/s\n", bps, 2 * n / ms / 1e6);
+        ms = time_it([&] { k_dot32<<<blocks, threads>>>(out, in); });        printf("blocks/SM-wave %d: dot3_32 %8.2f G dot/s\n", bps, n / ms / 1e6);
+        ms = time_it([&] { k_dot29<<<blocks, threads>>>(out, in); });        printf("blocks/SM-wave %d: dot3_29 %8.2f G dot/s\n", bps, n / ms / 1e6);
+        cudaFree(out);
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
