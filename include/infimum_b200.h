@@ -159,6 +159,19 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
                         uint64_t shift, const void* d_in, uint64_t n_in, void* d_out,
                         uint64_t* n_out, void* stream);
 
+/* State of the tree after the inserts, WITHOUT merging: the frontier the
+ * reference persists in `PollStateTree.hashes` (state.rs:85-86) — the (level,
+ * hash) pairs left by new(..) + insert(leaf) for every leaf (state.rs:176-225),
+ * levels non-increasing towards the tail — plus `depth` and, if the inserts
+ * completed the tree (state.rs:218-222), the root (then the frontier is empty).
+ *   out_levels   cap bytes, out_hashes cap*32 bytes; cap >= 4*33 always suffices
+ *   n_entries    number of frontier entries written
+ * Errors: TREE_ALREADY_FULL if more leaves than arity^full_depth. */
+int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                      const uint8_t* leaves, uint64_t n_leaves, uint8_t* out_levels,
+                      uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
+                      uint32_t* insert_depth, int* has_root, uint8_t root[32]);
+
 /* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
  * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */
 int inf_merge_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* leaves,

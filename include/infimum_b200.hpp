@@ -1,0 +1,437 @@
+// infimum_b200.hpp — C++ host-side mirror of the reference's interface for the
+// hot path, over the C ABI in infimum_b200.h.
+//
+// The reference is Rust; no Rust toolchain exists in the build image, so the
+// host side above the C ABI is written in C++ with the reference's names,
+// argument meaning and error behaviour, so that parity tests read like the
+// reference's own (tests/cpp/parity_tests.cpp vs pallet/src/tests/poseidon.rs
+// and pallet/src/tests/extrinsics.rs):
+//
+//   reference (Rust)                                   here (C++)
+//   Poseidon::<Fr>::new_circom(n)         poseidon.rs:304   infimum::Poseidon::new_circom(n)
+//   Poseidon::with_domain_tag_circom      poseidon.rs:309   infimum::Poseidon::with_domain_tag_circom
+//   PoseidonHasher::hash(&[Fr])           poseidon.rs:162   Poseidon::hash(std::vector<Fr>)
+//   PoseidonBytesHasher::hash_bytes_be/le poseidon.rs:213   Poseidon::hash_bytes_be / hash_bytes_le
+//   PoseidonError                         poseidon.rs:13    infimum::PoseidonError
+//   PollStateTree{depth,..,root}          state.rs:70       infimum::PollStateTree (same fields)
+//   AmortizedIncrementalMerkleTree::new/insert/merge/hash   state.rs:120   PollStateTree::new_/insert/merge/hash
+//   MerkleTreeError -> u8                 state.rs:94-118   infimum::MerkleTreeError (same codes)
+//   get_merkle_zeroes, EMPTY_BALLOT_ROOTS zeroes.rs:73-85   infimum::get_merkle_zeroes, empty_ballot_roots
+//   PollProvider::merge_registrations     provider.rs:289   infimum::merge_registrations
+//   PollProvider::merge_interactions      provider.rs:313   infimum::merge_interactions
+//
+// `Result<T,E>` is a minimal stand-in for Rust's.  Hashing only ever happens on
+// the GPU; the single piece of host arithmetic is Fr::from_be_bytes_mod_order's
+// reduction (<= 5 subtractions of p), needed so that Fr values compare equal.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "infimum_b200.h"
+
+namespace infimum {
+
+constexpr size_t HASH_LEN = 32;      // poseidon.rs:9
+constexpr size_t MAX_X5_LEN = 13;    // poseidon.rs:10
+using HashBytes = std::array<uint8_t, 32>;   // poll.rs:9
+
+// ---- Result ---------------------------------------------------------------------------
+template <class T, class E>
+class Result {
+    std::variant<T, E> v_;
+public:
+    Result(T t) : v_(std::in_place_index<0>, std::move(t)) {}
+    Result(E e) : v_(std::in_place_index<1>, std::move(e)) {}
+    bool is_ok() const { return v_.index() == 0; }
+    bool is_err() const { return v_.index() == 1; }
+    T& unwrap() {
+        if (!is_ok()) throw std::runtime_error("called unwrap() on an Err value");
+        return std::get<0>(v_);
+    }
+    const E& unwrap_err() const {
+        if (!is_err()) throw std::runtime_error("called unwrap_err() on an Ok value");
+        return std::get<1>(v_);
+    }
+    std::optional<T> ok() && { return is_ok() ? std::optional<T>(std::move(std::get<0>(v_))) : std::nullopt; }
+};
+
+// ---- errors ---------------------------------------------------------------------------
+struct PoseidonError {                                   // poseidon.rs:13-31
+    enum Kind { InvalidNumberOfInputs, EmptyInput, InvalidInputLength, BytesToPrimeFieldElement,
+                InputLargerThanModulus, VecToArray, U64ToU8, BytesToBigInt, InvalidWidthCircom } kind;
+    size_t inputs = 0, max_limit = 0, width = 0, len = 0, modulus_bytes_len = 0;
+    bool operator==(const PoseidonError& o) const {
+        return kind == o.kind && inputs == o.inputs && max_limit == o.max_limit && width == o.width &&
+               len == o.len && modulus_bytes_len == o.modulus_bytes_len;
+    }
+    static PoseidonError empty_input() { return PoseidonError{EmptyInput}; }
+    static PoseidonError invalid_input_length(size_t len) {
+        PoseidonError e{InvalidInputLength};
+        e.len = len; e.modulus_bytes_len = HASH_LEN;
+        return e;
+    }
+    static PoseidonError invalid_number_of_inputs(size_t inputs, size_t width) {
+        PoseidonError e{InvalidNumberOfInputs};
+        e.inputs = inputs; e.max_limit = width - 1; e.width = width;
+        return e;
+    }
+    static PoseidonError invalid_width_circom(size_t width) {
+        PoseidonError e{InvalidWidthCircom};
+        e.width = width; e.max_limit = MAX_X5_LEN;
+        return e;
+    }
+};
+
+enum class MerkleTreeError : uint8_t {                   // state.rs:94-118, u8 codes
+    TreeAlreadyFull = 1, TreeAlreadyMerged = 2, HashFailed = 3, MergeFailed = 4
+};
+inline uint8_t to_u8(MerkleTreeError e) { return static_cast<uint8_t>(e); }
+
+// ---- device context ---------------------------------------------------------------------
+class Context {
+    inf_ctx* ctx_ = nullptr;
+public:
+    explicit Context(int device = 0) {
+        int rc = inf_init(device, &ctx_);
+        if (rc != INF_OK)
+            throw std::runtime_error(std::string("inf_init failed: ") + inf_strerror(rc) +
+                                     " (infimum_b200 has no CPU fallback)");
+    }
+    ~Context() { inf_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    inf_ctx* get() const { return ctx_; }
+    static Context& global() {           // one per process, like the shim in INTEGRATION.md
+        static Context c(0);
+        return c;
+    }
+};
+
+// ---- Fr -----------------------------------------------------------------------------------
+// A field element as its canonical 32-byte big-endian encoding.
+struct Fr {
+    HashBytes be{};
+    static const HashBytes& modulus() {
+        static const HashBytes p = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45,
+                                    0xb6, 0x81, 0x81, 0x58, 0x5d, 0x28, 0x33, 0xe8, 0x48, 0x79, 0xb9,
+                                    0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01};
+        return p;
+    }
+    static Fr zero() { return Fr{}; }
+    static Fr one() { return from(1); }
+    static Fr from(uint64_t x) {
+        Fr r;
+        for (int i = 0; i < 8; i++) r.be[31 - i] = (uint8_t)(x >> (8 * i));
+        return r;
+    }
+    // Fr::from_be_bytes_mod_order for up to 32 bytes (state.rs:290, tests/poseidon.rs:26)
+    static Fr from_be_bytes_mod_order(const uint8_t* b, size_t n) {
+        if (n > 32) throw std::invalid_argument("from_be_bytes_mod_order: more than 32 bytes");
+        Fr r;
+        memcpy(r.be.data() + (32 - n), b, n);
+        const HashBytes& p = modulus();
+        while (memcmp(r.be.data(), p.data(), 32) >= 0) {
+            int borrow = 0;
+            for (int i = 31; i >= 0; i--) {
+                int d = (int)r.be[i] - (int)p[i] - borrow;
+                borrow = d < 0;
+                r.be[i] = (uint8_t)(d + (borrow << 8));
+            }
+        }
+        return r;
+    }
+    template <class C> static Fr from_be_bytes_mod_order(const C& c) { return from_be_bytes_mod_order(c.data(), c.size()); }
+    static Fr from_le_bytes_mod_order(const uint8_t* b, size_t n) {
+        std::vector<uint8_t> t(b, b + n);
+        for (size_t i = 0; i < n / 2; i++) std::swap(t[i], t[n - 1 - i]);
+        return from_be_bytes_mod_order(t.data(), n);
+    }
+    HashBytes to_bytes_be() const { return be; }         // into_bigint().to_bytes_be()
+    HashBytes to_bytes_le() const {
+        HashBytes r;
+        for (int i = 0; i < 32; i++) r[i] = be[31 - i];
+        return r;
+    }
+    bool is_zero() const { for (uint8_t x : be) if (x) return false; return true; }
+    bool operator==(const Fr& o) const { return be == o.be; }
+    bool operator!=(const Fr& o) const { return !(*this == o); }
+    std::string to_string() const {                      // decimal, like into_bigint().to_string()
+        std::array<uint8_t, 32> t = be;
+        std::string s;
+        for (;;) {
+            int rem = 0; bool nz = false;
+            for (int i = 0; i < 32; i++) {
+                int cur = rem * 256 + t[i];
+                t[i] = (uint8_t)(cur / 10); rem = cur % 10;
+                nz |= t[i] != 0;
+            }
+            s.insert(s.begin(), (char)('0' + rem));
+            if (!nz) break;
+        }
+        return s;
+    }
+};
+
+inline PoseidonError poseidon_error_from(int rc, size_t inputs, size_t width) {
+    switch (rc) {
+        case INF_ERR_INVALID_NUMBER_OF_INPUTS: return PoseidonError::invalid_number_of_inputs(inputs, width);
+        case INF_ERR_EMPTY_INPUT: return PoseidonError::empty_input();
+        case INF_ERR_INVALID_INPUT_LENGTH: return PoseidonError::invalid_input_length(0);
+        case INF_ERR_INVALID_WIDTH_CIRCOM: return PoseidonError::invalid_width_circom(width);
+        default: return PoseidonError{PoseidonError::BytesToBigInt};      // device failure
+    }
+}
+
+// ---- Poseidon -----------------------------------------------------------------------------
+class Poseidon {
+    size_t width_;
+    Fr domain_tag_;
+    Context* ctx_;
+    Poseidon(size_t width, Fr tag, Context* ctx) : width_(width), domain_tag_(tag), ctx_(ctx) {}
+    const uint8_t* tag_ptr(HashBytes& scratch, bool le) const {
+        if (domain_tag_.is_zero()) return nullptr;
+        scratch = le ? domain_tag_.to_bytes_le() : domain_tag_.be;
+        return scratch.data();
+    }
+public:
+    static Result<Poseidon, PoseidonError> new_circom(size_t nr_inputs, Context* ctx = nullptr) {
+        return with_domain_tag_circom(nr_inputs, Fr::zero(), ctx);
+    }
+    static Result<Poseidon, PoseidonError> with_domain_tag_circom(size_t nr_inputs, Fr domain_tag,
+                                                                  Context* ctx = nullptr) {
+        const size_t width = nr_inputs + 1;
+        if (width > MAX_X5_LEN || width < 2) return PoseidonError::invalid_width_circom(width);
+        return Poseidon(width, domain_tag, ctx ? ctx : &Context::global());
+    }
+    size_t width() const { return width_; }
+
+    // PoseidonHasher::hash
+    Result<Fr, PoseidonError> hash(const std::vector<Fr>& inputs) {
+        if (inputs.size() != width_ - 1) return PoseidonError::invalid_number_of_inputs(inputs.size(), width_);
+        std::vector<uint8_t> buf(inputs.size() * 32);
+        for (size_t i = 0; i < inputs.size(); i++) memcpy(&buf[32 * i], inputs[i].be.data(), 32);
+        Fr out;
+        HashBytes tag;
+        int rc = inf_poseidon_hash_batch(ctx_->get(), (uint32_t)inputs.size(), 0, tag_ptr(tag, false), buf.data(),
+                                         1, out.be.data());
+        if (rc) return poseidon_error_from(rc, inputs.size(), width_);
+        return out;
+    }
+
+    // n independent hashes over dense big-endian rows
+    Result<std::vector<HashBytes>, PoseidonError> hash_batch(const uint8_t* rows, uint64_t n) {
+        std::vector<HashBytes> out(n);
+        HashBytes tag;
+        int rc = inf_poseidon_hash_batch(ctx_->get(), (uint32_t)(width_ - 1), 0, tag_ptr(tag, false), rows, n,
+                                         n ? out[0].data() : nullptr);
+        if (rc) return poseidon_error_from(rc, width_ - 1, width_);
+        return out;
+    }
+
+    // PoseidonBytesHasher
+    using Slice = std::pair<const uint8_t*, size_t>;
+    Result<HashBytes, PoseidonError> hash_bytes_be(const std::vector<Slice>& inputs) { return hash_bytes(inputs, 0); }
+    Result<HashBytes, PoseidonError> hash_bytes_le(const std::vector<Slice>& inputs) {
+        return hash_bytes(inputs, INF_FLAG_LITTLE_ENDIAN);
+    }
+
+private:
+    Result<HashBytes, PoseidonError> hash_bytes(const std::vector<Slice>& inputs, uint32_t flags) {
+        // every input is converted before hash() counts them (poseidon.rs:215-226)
+        for (const Slice& s : inputs) {
+            if (s.second == 0) return PoseidonError::empty_input();
+            if (s.second != HASH_LEN) return PoseidonError::invalid_input_length(s.second);
+        }
+        if (inputs.size() != width_ - 1) return PoseidonError::invalid_number_of_inputs(inputs.size(), width_);
+        std::vector<const uint8_t*> ptrs;
+        std::vector<size_t> lens;
+        for (const Slice& s : inputs) { ptrs.push_back(s.first); lens.push_back(s.second); }
+        HashBytes out, tag;
+        int rc = inf_poseidon_hash_bytes(ctx_->get(), flags, tag_ptr(tag, flags != 0), ptrs.data(), lens.data(),
+                                         (uint32_t)inputs.size(), out.data());
+        if (rc) return poseidon_error_from(rc, inputs.size(), width_);
+        return out;
+    }
+};
+
+// ---- zero tables ------------------------------------------------------------------------------
+inline std::array<HashBytes, 33> get_merkle_zeroes(uint8_t arity, Context* ctx = nullptr) {   // zeroes.rs:81-85
+    std::array<HashBytes, 33> z;
+    inf_merkle_zeroes((ctx ? ctx : &Context::global())->get(), arity, z[0].data());
+    return z;
+}
+inline std::array<HashBytes, 5> empty_ballot_roots() {                                         // zeroes.rs:73-79
+    std::array<HashBytes, 5> r;
+    inf_empty_ballot_roots(r[0].data());
+    return r;
+}
+
+// ---- PollStateTree ------------------------------------------------------------------------------
+// Same fields as the reference struct (state.rs:70-91).  The reference hashes
+// inside insert() and keeps only the frontier; here insert() buffers the leaf
+// and the device does all the hashing in merge() (or when the last insert
+// completes the tree).  `hashes` is materialised on request by frontier().
+struct PollStateTree {
+    uint8_t depth = 0;
+    uint8_t full_depth = 0;
+    uint8_t arity = 0;
+    uint32_t count = 0;
+    std::vector<std::pair<uint8_t, HashBytes>> hashes;    // filled by frontier(); empty once merged
+    std::optional<HashBytes> root;
+
+    static PollStateTree new_(uint8_t arity, uint8_t full_depth,
+                              std::optional<std::pair<uint8_t, HashBytes>> zero_hash, Context* ctx = nullptr) {
+        PollStateTree t;
+        t.arity = arity;
+        t.full_depth = full_depth;
+        t.ctx_ = ctx ? ctx : &Context::global();
+        if (zero_hash) {
+            // the pallet only ever seeds (0, zeroes[0]) (state.rs:48-52)
+            if (zero_hash->first != 0 || zero_hash->second != get_merkle_zeroes(arity, t.ctx_)[0])
+                throw std::invalid_argument("only the reference's seeding (level 0, zeroes[0]) is supported");
+            t.seeded_ = true;
+        }
+        return t;
+    }
+
+    Result<PollStateTree, MerkleTreeError> insert(const HashBytes& leaf) && {
+        return std::move(*this).extend(leaf.data(), 1);
+    }
+    // bulk insert of n leaves (dense 32-byte rows), in insertion order
+    Result<PollStateTree, MerkleTreeError> extend(const uint8_t* leaves, uint64_t n) && {
+        if (root) return MerkleTreeError::TreeAlreadyFull;                 // state.rs:182
+        const unsigned __int128 cap = capacity();
+        if ((unsigned __int128)total() + n > cap) return MerkleTreeError::TreeAlreadyFull;
+        leaves_.insert(leaves_.end(), leaves, leaves + 32 * n);
+        count += (uint32_t)n;
+        uint8_t d = 0;
+        while (d < full_depth && ipow(d + 1) <= total()) d++;
+        depth = d;                                                         // state.rs:212-213
+        if ((unsigned __int128)total() == cap) {                           // state.rs:218-222
+            int rc = run_merge(true);
+            if (rc != INF_OK && rc != INF_ERR_TREE_ALREADY_MERGED) return tree_error(rc);
+        }
+        return std::move(*this);
+    }
+    Result<PollStateTree, MerkleTreeError> merge(bool to_depth) && {       // state.rs:230-281
+        if (root) return MerkleTreeError::TreeAlreadyMerged;
+        int rc = run_merge(to_depth);
+        if (rc != INF_OK) return tree_error(rc);
+        return std::move(*this);
+    }
+    // state.rs:284-302
+    static Result<HashBytes, PoseidonError> hash(const std::vector<HashBytes>& inputs, Context* ctx = nullptr) {
+        auto h = Poseidon::new_circom(inputs.size(), ctx);
+        if (h.is_err()) return h.unwrap_err();
+        std::vector<Poseidon::Slice> s;
+        for (const HashBytes& b : inputs) s.push_back({b.data(), b.size()});
+        return h.unwrap().hash_bytes_be(s);
+    }
+    // Materialise `hashes` (the reference's persisted frontier) for the leaves inserted so far.
+    Result<PollStateTree, MerkleTreeError> frontier() && {
+        hashes.clear();
+        if (root) return std::move(*this);
+        uint8_t levels[4 * 33];
+        std::vector<uint8_t> hs(4 * 33 * 32);
+        uint32_t n = 0, idepth = 0;
+        int has = 0;
+        HashBytes r;
+        int rc = inf_tree_frontier(ctx_->get(), arity, full_depth, seeded_, leaves_.data(), count, levels, hs.data(),
+                                   4 * 33, &n, &idepth, &has, r.data());
+        if (rc) return tree_error(rc);
+        for (uint32_t i = 0; i < n; i++) {
+            HashBytes h;
+            memcpy(h.data(), &hs[32 * i], 32);
+            hashes.push_back({levels[i], h});
+        }
+        return std::move(*this);
+    }
+
+private:
+    Context* ctx_ = nullptr;
+    bool seeded_ = false;
+    std::vector<uint8_t> leaves_;
+    uint64_t total() const { return (uint64_t)count + (seeded_ ? 1 : 0); }
+    unsigned __int128 capacity() const {
+        unsigned __int128 c = 1;
+        for (int i = 0; i < full_depth; i++) c *= arity;
+        return c;
+    }
+    uint64_t ipow(int e) const {
+        unsigned __int128 c = 1;
+        for (int i = 0; i < e; i++) { c *= arity; if (c > (unsigned __int128)UINT64_MAX) return UINT64_MAX; }
+        return (uint64_t)c;
+    }
+    static MerkleTreeError tree_error(int rc) {
+        return (rc >= 1 && rc <= 4) ? static_cast<MerkleTreeError>(rc) : MerkleTreeError::HashFailed;
+    }
+    int run_merge(bool to_depth) {
+        HashBytes r;
+        uint32_t idepth = 0, rdepth = 0;
+        int has = 0;
+        int rc = inf_tree_merge(ctx_->get(), arity, full_depth, seeded_, to_depth, leaves_.data(), count, r.data(),
+                                &idepth, &rdepth, &has);
+        if (rc == INF_OK || rc == INF_ERR_TREE_ALREADY_MERGED) {
+            if (has) {
+                root = r;
+                hashes.clear();
+                leaves_.clear();
+                leaves_.shrink_to_fit();
+            }
+            depth = (uint8_t)idepth;
+        }
+        return rc;
+    }
+};
+
+// PollState::new (state.rs:42-67): the two trees of a poll
+inline PollStateTree new_registration_tree(uint8_t registration_depth, Context* ctx = nullptr) {
+    return PollStateTree::new_(2, registration_depth, std::make_pair((uint8_t)0, get_merkle_zeroes(2, ctx)[0]), ctx);
+}
+inline PollStateTree new_interaction_tree(uint8_t interaction_depth, Context* ctx = nullptr) {
+    return PollStateTree::new_(5, interaction_depth, std::nullopt, ctx);
+}
+
+// ---- provider.rs:289-327 ------------------------------------------------------------------------------
+struct Commitment {                                      // coordinator.rs (subset used here)
+    std::pair<uint32_t, HashBytes> process{0, HashBytes{}};
+    uint32_t expected_process = 0, expected_tally = 0;
+};
+
+// merge_registrations: registrations.merge(false), then
+// commitment.process = (0, H3(root, EMPTY_BALLOT_ROOTS[1], 0))
+inline Result<std::pair<PollStateTree, Commitment>, MerkleTreeError>
+merge_registrations(PollStateTree registrations, Commitment commitment = {}) {
+    auto m = std::move(registrations).merge(false);
+    if (m.is_err()) return m.unwrap_err();
+    PollStateTree t = std::move(m.unwrap());
+    if (!t.root) return MerkleTreeError::MergeFailed;
+    auto h = PollStateTree::hash({*t.root, empty_ballot_roots()[1], HashBytes{}});
+    if (h.is_err()) return MerkleTreeError::HashFailed;
+    commitment.process = {0, h.unwrap()};
+    return std::make_pair(std::move(t), commitment);
+}
+
+// merge_interactions: interactions.merge(true) and the expected proof counts
+inline Result<std::pair<PollStateTree, Commitment>, MerkleTreeError>
+merge_interactions(PollStateTree interactions, uint32_t registrations_count, uint8_t process_subtree_depth,
+                   uint8_t tally_subtree_depth, Commitment commitment = {}) {
+    auto m = std::move(interactions).merge(true);
+    if (m.is_err()) return m.unwrap_err();
+    PollStateTree t = std::move(m.unwrap());
+    uint32_t pb = 1, tb = 1;
+    for (int i = 0; i < process_subtree_depth; i++) pb *= t.arity;
+    for (int i = 0; i < tally_subtree_depth; i++) tb *= 2;
+    commitment.expected_process = t.count / pb + ((t.count % pb) ? 1 : 0);
+    commitment.expected_tally = 1 + registrations_count / tb;
+    return std::make_pair(std::move(t), commitment);
+}
+
+}  // namespace infimum

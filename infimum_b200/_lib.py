@@ -35,7 +35,7 @@ EXPORTS = [
     "inf_init", "inf_destroy", "inf_strerror", "inf_last_cuda_error", "inf_version",
     "inf_poseidon_hash_batch", "inf_poseidon_hash_batch_dev", "inf_poseidon_hash_bytes",
     "inf_poseidon_hash_batch_dense", "inf_merkle_zeroes", "inf_empty_ballot_roots",
-    "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_merge_registrations",
+    "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_tree_frontier", "inf_merge_registrations",
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
     "inf_measure_imad_peak",
 ]
@@ -90,6 +90,9 @@ def load() -> C.CDLL:
     lib.inf_tree_reduce_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp,
                                         u64p, vp]
     lib.inf_tree_reduce_dev.restype = C.c_int
+    lib.inf_tree_frontier.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_uint64, vp, vp, C.c_uint32, u32p,
+                                      u32p, ip, vp]
+    lib.inf_tree_frontier.restype = C.c_int
     lib.inf_merge_registrations.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, u32p]
     lib.inf_merge_registrations.restype = C.c_int
     lib.inf_merge_interactions.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -510,6 +510,81 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
     return INF_OK;
 }
 
+int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                      const uint8_t* leaves, uint64_t n_leaves, uint8_t* out_levels,
+                      uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
+                      uint32_t* insert_depth, int* has_root, uint8_t root[32]) {
+    if (!ctx || !n_entries) return INF_ERR_NULL_POINTER;
+    if (n_leaves && !leaves) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    *n_entries = 0;
+    if (insert_depth) *insert_depth = 0;
+    if (has_root) *has_root = 0;
+    const uint64_t shift = prepend_blank_leaf ? 1 : 0;
+    const uint64_t n_total = n_leaves + shift;
+    const uint64_t capacity = pow_sat(arity, full_depth);
+    if (n_total > capacity) return INF_ERR_TREE_ALREADY_FULL;
+    if (n_total == 0) return INF_OK;
+    Bind bind(ctx);
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (n_leaves) {
+        if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32))) return rc;
+        CU(cudaMemcpyAsync(ctx->io[0], leaves, (size_t)n_leaves * 32, cudaMemcpyHostToDevice, st));
+    }
+    // Full nodes only: level d has floor(n_total / arity^d) of them; the
+    // frontier keeps the trailing (that count mod arity) of each level — the
+    // base-arity digits of n_total — highest level first.
+    struct Lvl { const char* nodes; uint64_t n_full; uint64_t sh; };
+    std::vector<Lvl> lv;
+    const uint64_t n1 = n_total / arity, n2 = n1 / arity;
+    if ((rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], std::max<uint64_t>(n1, 1) * 32))) return rc;
+    if ((rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], std::max<uint64_t>(n2, 1) * 32))) return rc;
+    // every level's trailing nodes are copied out as soon as the level exists
+    std::vector<uint8_t> tail_levels;
+    std::vector<std::vector<uint8_t>> tails;      // per level, digit * 32 bytes
+    const char* cur = (const char*)ctx->io[0];
+    uint64_t n_cur = n_total, sh = shift;         // n_cur counts logical nodes (shift included)
+    uint32_t d = 0;
+    for (;; d++) {
+        const uint64_t digit = n_cur % arity, n_next = n_cur / arity;
+        std::vector<uint8_t> t(digit * 32);
+        for (uint64_t k = 0; k < digit; k++) {
+            const uint64_t j = n_cur - digit + k;           // logical index at this level
+            if (j < sh) memcpy(&t[k * 32], Z[d], 32);       // the blank leaf itself (level 0 only)
+            else CU(cudaMemcpyAsync(&t[k * 32], cur + (j - sh) * 32, 32, cudaMemcpyDeviceToHost, st));
+        }
+        tails.push_back(std::move(t));
+        if (n_next == 0) break;
+        char* dst = (char*)ctx->scratch[d & 1];
+        CU(launch_level(arity, cur, sh, n_cur - sh, dst, n_next, Z[d], st));   // reads only the first arity*n_next logical nodes
+        cur = dst;
+        n_cur = n_next;
+        sh = 0;
+    }
+    CU(cudaStreamSynchronize(st));
+    uint32_t idepth = d;                                    // highest level reached by the cascade
+    if (insert_depth) *insert_depth = idepth;
+    if (n_total == capacity) {                              // completed by insert: root, empty frontier
+        if (has_root) *has_root = 1;
+        if (root) memcpy(root, tails.back().data(), 32);
+        return INF_OK;
+    }
+    uint32_t n = 0;
+    for (int l = (int)tails.size() - 1; l >= 0; l--) {
+        for (size_t k = 0; k * 32 < tails[l].size(); k++) {
+            if (n >= cap || !out_levels || !out_hashes) return INF_ERR_NULL_POINTER;
+            out_levels[n] = (uint8_t)l;
+            memcpy(out_hashes + 32 * n, &tails[l][k * 32], 32);
+            n++;
+        }
+    }
+    *n_entries = n;
+    return INF_OK;
+}
+
 int inf_merge_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* leaves,
                             uint64_t n_leaves, uint8_t root[32], uint8_t process_commitment[32],
                             uint32_t* insert_depth) {

@@ -68,11 +68,24 @@ class PollStateTree:
 
     @property
     def hashes(self) -> List[Tuple[int, bytes]]:
-        """Frontier.  Empty once `root` is set, as in the reference; before the
-        merge it is not materialised by this host mirror."""
+        """The frontier `PollStateTree.hashes` (state.rs:85-86): empty once
+        `root` is set; before that, the (level, hash) pairs the reference's
+        insert cascade would have left, computed on the device from the
+        buffered leaves (inf_tree_frontier)."""
         if self.root is not None:
             return []
-        raise NotImplementedError("frontier of an unmerged tree is not materialised on this path")
+        lv = self._leaves()
+        cap = 4 * 33
+        levels = C.create_string_buffer(cap)
+        hashes = C.create_string_buffer(cap * 32)
+        n, idepth, has = C.c_uint32(), C.c_uint32(), C.c_int()
+        root = C.create_string_buffer(32)
+        rc = self.ctx.lib.inf_tree_frontier(self.ctx.handle, self.arity, self.full_depth,
+                                            1 if self._seed is not None else 0,
+                                            lv.ctypes.data if lv.size else None, lv.shape[0], levels, hashes, cap,
+                                            C.byref(n), C.byref(idepth), C.byref(has), root)
+        self.ctx.check(rc)
+        return [(levels.raw[i], hashes.raw[32 * i:32 * i + 32]) for i in range(n.value)]
 
     def _total(self) -> int:
         return self.count + (1 if self._seed is not None else 0)

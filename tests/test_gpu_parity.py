@@ -311,3 +311,49 @@ def test_full_size_properties_2_24(ib):
     left = ib.PollStateTree.new(2, 23).extend(leaves[: n // 2]).root
     right = ib.PollStateTree.new(2, 23).extend(leaves[n // 2:]).root
     assert whole == c_oracle.hash_one([left, right])
+
+
+# ---- frontier (`PollStateTree.hashes` before the merge, state.rs:85-86) -----------------------
+@pytest.mark.parametrize("arity,full_depth,blank", [(2, 11, True), (5, 5, False), (2, 11, False), (5, 5, True)])
+def test_frontier_equals_insert_cascade(ib, arity, full_depth, blank):
+    allv = random_fr_bytes(700, seed=arity + 40)
+    for n in [0, 1, 2, 3, 4, 5, 6, 7, 8, 24, 25, 26, 31, 32, 33, 124, 125, 126, 255, 256, 511, 624, 625, 626, 700]:
+        leaves = allv[:n]
+        o = O.PollStateTree.new(arity, full_depth, (0, O.merkle_zeroes(arity)[0]) if blank else None)
+        for i in range(n):
+            o.insert(leaves[i].tobytes())
+        t = ib.PollStateTree.new(arity, full_depth, (0, ib.get_merkle_zeroes(arity)[0]) if blank else None)
+        t.extend(leaves)
+        assert t.hashes == o.hashes, (arity, n)
+        assert (t.depth, t.count) == (o.depth, o.count)
+
+
+def test_hypothesis_tree_and_reduction_properties(ib):
+    """gpu_tree(leaves) == oracle insert*N + merge, and
+    hash(x) == hash(x + p) for x < 2^256 - p, on hypothesis-drawn cases."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    h2 = ib.Poseidon.new_circom(2)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, (1 << 256) - 1 - P), st.integers(0, (1 << 256) - 1))
+    def reduction(x, y):
+        a = h2.hash_batch(be(x) + be(y))
+        b = h2.hash_batch(be(x + P) + be(y))
+        assert (a == b).all()
+        assert a.tobytes() == c_oracle.hash_one([be(x), be(y)])
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.sampled_from([2, 5]), st.integers(0, 400), st.booleans(), st.booleans(), st.integers(0, 2 ** 32))
+    def tree(arity, n, blank, to_depth, seed):
+        full_depth = 9 if arity == 2 else 4
+        if n + blank >= arity ** full_depth:
+            n = arity ** full_depth - 2
+        leaves = random_fr_bytes(max(n, 1), seed=seed, canonical=False)[:n]
+        rc, root, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
+        t = ib.PollStateTree.new(arity, full_depth, (0, ib.get_merkle_zeroes(arity)[0]) if blank else None)
+        t.extend(leaves).merge(to_depth)
+        assert rc == 0 and t.root == root and (t.depth, t.count) == (depth, count)
+
+    reduction()
+    tree()
