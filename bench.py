@@ -380,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
                        "shard_level": plan.level, "subtrees": plan.n_subtrees,
                        "collective": "one all_gather of <=%d x 32 B subtree roots per rank (NCCL)" %
                                      max(e - b for b, e in plan.subtree_ranges) if world > 1 else "none (1 GPU)",
-                       "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / peak,
+                       "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / (peak * world),
                        "root": root_hex},
         "bit_exact_sample": ok,
     }

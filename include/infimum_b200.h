@@ -109,6 +109,25 @@ int inf_poseidon_hash_batch_dense(inf_ctx* ctx, uint32_t n_inputs, uint32_t flag
                                   const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
                                   uint8_t* out);
 
+/* ---- leaf hashing (the step before the trees) ------------------------------------
+ * Registration leaves, PollProvider::register_participant (provider.rs:218-241):
+ *     leaf[i] = hash4(pk[i].x, pk[i].y, 1, timestamp[i])
+ * Interaction leaves, PollProvider::consume_interaction (provider.rs:243-287):
+ *     leaf[i] = hash4(hash5(d[i][0..5]), hash5(d[i][5..10]), pk[i].x, pk[i].y)
+ *   public_keys  n * 64 bytes: `PublicKey {x, y}` (keys.rs), 32-byte big-endian each
+ *   timestamps   n * u64 (the block number the reference passes)
+ *   data         n * 320 bytes: `PollInteractionData = [[u8;32];10]` (poll.rs)
+ *   leaves       n * 32 bytes out
+ * The `_dev` forms take device pointers and enqueue on `stream`. */
+int inf_registration_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint64_t* timestamps,
+                            uint64_t n, uint8_t* leaves);
+int inf_interaction_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint8_t* data, uint64_t n,
+                           uint8_t* leaves);
+int inf_registration_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const void* d_timestamps,
+                                uint64_t n, void* d_leaves, void* stream);
+int inf_interaction_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const void* d_data,
+                               uint64_t n, void* d_leaves, void* stream);
+
 /* ---- Merkle zero tables -------------------------------------------------------
  * get_merkle_zeroes(arity) (zeroes.rs:81-85): 33 x 32 bytes; arity 2 -> binary
  * table, anything else -> quinary table.  EMPTY_BALLOT_ROOTS: 5 x 32 bytes. */
@@ -171,6 +190,30 @@ int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pre
                       const uint8_t* leaves, uint64_t n_leaves, uint8_t* out_levels,
                       uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
                       uint32_t* insert_depth, int* has_root, uint8_t root[32]);
+
+/* ---- retained trees and Merkle paths ------------------------------------------------
+ * inf_tree_build keeps every level of the dense, zero-padded tree of `depth`
+ * levels over the leaves on the device (the batch equivalent of the tree the
+ * reference only keeps a frontier of), so sibling paths can be served in bulk —
+ * what the off-chain coordinator feeds the circuits
+ * (circuits/process-messages.circom:57,85).  Path layout = the argument of
+ * compute_merkle_root_from_path (provider.rs:396-436): for every level the
+ * arity-1 siblings in order, the node's own position skipped;
+ * n_idx * depth * (arity-1) * 32 bytes.  Leaf indices count the blank leaf (it
+ * is leaf 0 when prepend_blank_leaf is set). */
+typedef struct inf_tree inf_tree;
+int inf_tree_build(inf_ctx* ctx, uint32_t arity, uint32_t depth, int prepend_blank_leaf,
+                   const uint8_t* leaves, uint64_t n_leaves, inf_tree** out);
+int inf_tree_root(inf_tree* tree, uint8_t root[32]);
+int inf_tree_paths(inf_tree* tree, const uint64_t* leaf_indices, uint64_t n_idx, uint8_t* paths);
+void inf_tree_destroy(inf_tree* tree);
+
+/* compute_merkle_root_from_path (provider.rs:396-436), batched: n paths of
+ * `depth` levels, arity 5 as in the reference (VOTE_TREE_ARITY) or 2.
+ *   indices  n leaf indices; leaves n*32; paths n*depth*(arity-1)*32; roots n*32 out */
+int inf_merkle_roots_from_paths(inf_ctx* ctx, uint32_t arity, uint32_t depth, const uint64_t* indices,
+                                const uint8_t* leaves, const uint8_t* paths, uint64_t n,
+                                uint8_t* roots);
 
 /* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
  * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */

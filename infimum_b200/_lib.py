@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libinfimum_b200.so")
+# INFIMUM_B200_LIB: load another build of the same library (kernel-variant experiments)
+LIB_PATH = os.environ.get("INFIMUM_B200_LIB") or os.path.join(HERE, "libinfimum_b200.so")
 
 # return codes (include/infimum_b200.h)
 OK = 0
@@ -34,8 +35,10 @@ FLAG_LITTLE_ENDIAN = 1
 EXPORTS = [
     "inf_init", "inf_destroy", "inf_strerror", "inf_last_cuda_error", "inf_version",
     "inf_poseidon_hash_batch", "inf_poseidon_hash_batch_dev", "inf_poseidon_hash_bytes",
-    "inf_poseidon_hash_batch_dense", "inf_merkle_zeroes", "inf_empty_ballot_roots",
-    "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_tree_frontier", "inf_merge_registrations",
+    "inf_poseidon_hash_batch_dense", "inf_registration_leaves", "inf_interaction_leaves",
+    "inf_registration_leaves_dev", "inf_interaction_leaves_dev", "inf_merkle_zeroes", "inf_empty_ballot_roots",
+    "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_tree_frontier", "inf_tree_build", "inf_tree_root", "inf_tree_paths",
+    "inf_tree_destroy", "inf_merkle_roots_from_paths", "inf_merge_registrations",
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
     "inf_measure_imad_peak",
 ]
@@ -78,6 +81,14 @@ def load() -> C.CDLL:
     lib.inf_poseidon_hash_bytes.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
                                             C.c_uint32, vp]
     lib.inf_poseidon_hash_bytes.restype = C.c_int
+    lib.inf_registration_leaves.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.inf_registration_leaves.restype = C.c_int
+    lib.inf_interaction_leaves.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.inf_interaction_leaves.restype = C.c_int
+    lib.inf_registration_leaves_dev.argtypes = [vp, vp, vp, C.c_uint64, vp, vp]
+    lib.inf_registration_leaves_dev.restype = C.c_int
+    lib.inf_interaction_leaves_dev.argtypes = [vp, vp, vp, C.c_uint64, vp, vp]
+    lib.inf_interaction_leaves_dev.restype = C.c_int
     lib.inf_merkle_zeroes.argtypes = [vp, C.c_uint32, vp]
     lib.inf_merkle_zeroes.restype = C.c_int
     lib.inf_empty_ballot_roots.argtypes = [vp]
@@ -93,6 +104,16 @@ def load() -> C.CDLL:
     lib.inf_tree_frontier.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_uint64, vp, vp, C.c_uint32, u32p,
                                       u32p, ip, vp]
     lib.inf_tree_frontier.restype = C.c_int
+    lib.inf_tree_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_uint64, C.POINTER(vp)]
+    lib.inf_tree_build.restype = C.c_int
+    lib.inf_tree_root.argtypes = [vp, vp]
+    lib.inf_tree_root.restype = C.c_int
+    lib.inf_tree_paths.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.inf_tree_paths.restype = C.c_int
+    lib.inf_tree_destroy.argtypes = [vp]
+    lib.inf_tree_destroy.restype = None
+    lib.inf_merkle_roots_from_paths.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]
+    lib.inf_merkle_roots_from_paths.restype = C.c_int
     lib.inf_merge_registrations.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, u32p]
     lib.inf_merge_registrations.restype = C.c_int
     lib.inf_merge_interactions.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -24,6 +24,17 @@ cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double*
 
 using namespace inf;
 
+struct inf_tree {
+    inf_ctx* ctx = nullptr;
+    uint32_t arity = 0, depth = 0;
+    uint64_t shift = 0, n_leaves = 0;
+    void* d_nodes = nullptr;                   // all levels 0..depth back to back (level 0 = logical leaves)
+    std::vector<uint64_t> offsets, counts;     // per level, in nodes
+    void* d_level_ptrs = nullptr;              // device copies for the gather kernel
+    void* d_level_counts = nullptr;
+    void* d_zero_nodes = nullptr;
+};
+
 struct inf_ctx {
     int device = -1;
     int sm_count = 0;
@@ -231,6 +242,35 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
     return completed_by_insert ? INF_ERR_TREE_ALREADY_MERGED : INF_OK;   // merge(): state.rs:236
 }
 
+// Generic chunked pipeline for per-row kernels with up to two host inputs:
+// rows rotate over the three pipeline streams as H2D -> kernel -> D2H.
+template <class Launch>
+int rows_pipeline(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* in1, size_t row1,
+                         uint64_t n, uint8_t* out, Launch launch) {
+    const uint64_t super = 1ull << 22, chunk = 1ull << 17;
+    const uint64_t n_stage = std::min<uint64_t>(n, super);
+    int rc;
+    // staging: io[0] holds both inputs back to back, io[1] the output
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_stage * (row0 + row1)))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], n_stage * 32))) return rc;
+    char* s0 = (char*)ctx->io[0];
+    char* s1 = s0 + n_stage * row0;
+    for (uint64_t base = 0; base < n; base += super) {
+        const uint64_t m = std::min<uint64_t>(super, n - base);
+        int k = 0;
+        for (uint64_t off = 0; off < m; off += chunk, k++) {
+            const uint64_t c = std::min<uint64_t>(chunk, m - off);
+            cudaStream_t st = ctx->pipe[k % 3];
+            CU(cudaMemcpyAsync(s0 + off * row0, in0 + (base + off) * row0, c * row0, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s1 + off * row1, in1 + (base + off) * row1, c * row1, cudaMemcpyHostToDevice, st));
+            CU(launch(s0 + off * row0, s1 + off * row1, (char*)ctx->io[1] + off * 32, c, st));
+            CU(cudaMemcpyAsync(out + (base + off) * 32, (char*)ctx->io[1] + off * 32, c * 32, cudaMemcpyDeviceToHost, st));
+        }
+        for (int i = 0; i < 3; i++) CU(cudaStreamSynchronize(ctx->pipe[i]));
+    }
+    return INF_OK;
+}
+
 std::mutex g_init_mu;
 
 }  // namespace
@@ -294,6 +334,11 @@ int inf_init(int device, inf_ctx** out) {
             std::vector<uint32_t> tbl = host::build_opt_table(t);
             if ((e = uploaders[t](tbl.data(), tbl.size())) != cudaSuccess)
                 return fail(cuda_fail(nullptr, e, "upload optimised table"));
+        }
+        {
+            std::vector<uint32_t> t5 = host::build_opt_table(5), t6 = host::build_opt_table(6);
+            if ((e = upload_leaf_tables(t5.data(), t5.size(), t6.data(), t6.size())) != cudaSuccess)
+                return fail(cuda_fail(nullptr, e, "upload leaf tables"));
         }
         for (int t = 2; t <= 13; t++) {
             std::vector<uint32_t> tbl = host::build_dense_table(t);
@@ -422,6 +467,49 @@ int inf_poseidon_hash_bytes(inf_ctx* ctx, uint32_t flags, const uint8_t* domain_
         memcpy(buf + 32 * i, inputs[i], 32);
     }
     return hash_batch_host(ctx, n_inputs, flags, domain_tag, buf, 1, out, false);
+}
+
+int inf_registration_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint64_t* timestamps,
+                            uint64_t n, uint8_t* leaves) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!public_keys || !timestamps || !leaves)) return INF_ERR_NULL_POINTER;
+    if (n == 0) return INF_OK;
+    Bind bind(ctx);
+    return rows_pipeline(ctx, public_keys, 64, (const uint8_t*)timestamps, 8, n, leaves,
+                         [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
+                             return launch_registration_leaves(a, b, o, c, st);
+                         });
+}
+
+int inf_interaction_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint8_t* data, uint64_t n,
+                           uint8_t* leaves) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!public_keys || !data || !leaves)) return INF_ERR_NULL_POINTER;
+    if (n == 0) return INF_OK;
+    Bind bind(ctx);
+    return rows_pipeline(ctx, public_keys, 64, data, 320, n, leaves,
+                         [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
+                             return launch_interaction_leaves(a, b, o, c, st);
+                         });
+}
+
+int inf_registration_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const void* d_timestamps,
+                                uint64_t n, void* d_leaves, void* stream) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!d_public_keys || !d_timestamps || !d_leaves)) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    CU(launch_registration_leaves(d_public_keys, d_timestamps, d_leaves, n,
+                                  stream ? (cudaStream_t)stream : ctx->stream));
+    return INF_OK;
+}
+
+int inf_interaction_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const void* d_data,
+                               uint64_t n, void* d_leaves, void* stream) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!d_public_keys || !d_data || !d_leaves)) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    CU(launch_interaction_leaves(d_public_keys, d_data, d_leaves, n, stream ? (cudaStream_t)stream : ctx->stream));
+    return INF_OK;
 }
 
 int inf_merkle_zeroes(inf_ctx* ctx, uint32_t arity, uint8_t out[33 * 32]) {
@@ -582,6 +670,121 @@ int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pre
         }
     }
     *n_entries = n;
+    return INF_OK;
+}
+
+int inf_tree_build(inf_ctx* ctx, uint32_t arity, uint32_t depth, int prepend_blank_leaf,
+                   const uint8_t* leaves, uint64_t n_leaves, inf_tree** out) {
+    if (!ctx || !out) return INF_ERR_NULL_POINTER;
+    *out = nullptr;
+    if (n_leaves && !leaves) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (depth > 32) return INF_ERR_BAD_DEPTH;
+    const uint64_t shift = prepend_blank_leaf ? 1 : 0, n_total = n_leaves + shift;
+    if (n_total > pow_sat(arity, depth)) return INF_ERR_TREE_ALREADY_FULL;
+    if (n_total == 0) return INF_ERR_MERGE_FAILED;             // nothing to build a tree over
+    Bind bind(ctx);
+    inf_tree* t = new inf_tree();
+    t->ctx = ctx; t->arity = arity; t->depth = depth; t->shift = shift; t->n_leaves = n_leaves;
+    uint64_t total_nodes = 0, c = n_total;
+    for (uint32_t l = 0; l <= depth; l++) {
+        t->offsets.push_back(total_nodes);
+        t->counts.push_back(c);
+        total_nodes += c;
+        c = (c + arity - 1) / arity;
+    }
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    cudaStream_t st = ctx->stream;
+    auto fail = [&](int rc) { inf_tree_destroy(t); return rc; };
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->d_nodes, total_nodes * 32)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc tree levels"));
+    if ((e = cudaMalloc(&t->d_level_ptrs, (depth + 1) * sizeof(void*))) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
+    if ((e = cudaMalloc(&t->d_level_counts, (depth + 1) * 8)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
+    if ((e = cudaMalloc(&t->d_zero_nodes, 33 * 32)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
+    std::vector<void*> ptrs;
+    for (uint32_t l = 0; l <= depth; l++) ptrs.push_back((char*)t->d_nodes + t->offsets[l] * 32);
+    // level 0 = [blank leaf] ++ leaves, materialised so that paths index one array
+    if (shift) e = cudaMemcpyAsync(t->d_nodes, Z[0], 32, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_leaves)
+        e = cudaMemcpyAsync((char*)t->d_nodes + shift * 32, leaves, n_leaves * 32, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_level_ptrs, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_level_counts, t->counts.data(), t->counts.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_zero_nodes, Z, 33 * 32, cudaMemcpyHostToDevice, st);
+    for (uint32_t l = 0; l < depth && e == cudaSuccess; l++)
+        e = launch_level(arity, ptrs[l], 0, t->counts[l], ptrs[l + 1], t->counts[l + 1], Z[l], st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "inf_tree_build"));
+    *out = t;
+    return INF_OK;
+}
+
+int inf_tree_root(inf_tree* tree, uint8_t root[32]) {
+    if (!tree || !root) return INF_ERR_NULL_POINTER;
+    inf_ctx* ctx = tree->ctx;
+    Bind bind(ctx);
+    CU(cudaMemcpy(root, (char*)tree->d_nodes + tree->offsets[tree->depth] * 32, 32, cudaMemcpyDeviceToHost));
+    return INF_OK;
+}
+
+int inf_tree_paths(inf_tree* tree, const uint64_t* leaf_indices, uint64_t n_idx, uint8_t* paths) {
+    if (!tree) return INF_ERR_NULL_POINTER;
+    if (n_idx && (!leaf_indices || !paths)) return INF_ERR_NULL_POINTER;
+    if (n_idx == 0 || tree->depth == 0) return INF_OK;
+    inf_ctx* ctx = tree->ctx;
+    Bind bind(ctx);
+    const uint64_t cap = pow_sat(tree->arity, tree->depth);
+    for (uint64_t i = 0; i < n_idx; i++)
+        if (leaf_indices[i] >= cap) return INF_ERR_BAD_DEPTH;
+    const size_t out_bytes = (size_t)n_idx * tree->depth * (tree->arity - 1) * 32;
+    int rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_idx * 8))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], out_bytes))) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->io[0], leaf_indices, n_idx * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_gather_paths((const void* const*)tree->d_level_ptrs, (const uint64_t*)tree->d_level_counts,
+                           tree->d_zero_nodes, tree->arity, tree->depth, ctx->io[0], n_idx, ctx->io[1], st));
+    CU(cudaMemcpyAsync(paths, ctx->io[1], out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return INF_OK;
+}
+
+void inf_tree_destroy(inf_tree* tree) {
+    if (!tree) return;
+    {
+        Bind bind(tree->ctx);
+        if (tree->d_nodes) cudaFree(tree->d_nodes);
+        if (tree->d_level_ptrs) cudaFree(tree->d_level_ptrs);
+        if (tree->d_level_counts) cudaFree(tree->d_level_counts);
+        if (tree->d_zero_nodes) cudaFree(tree->d_zero_nodes);
+    }
+    delete tree;
+}
+
+int inf_merkle_roots_from_paths(inf_ctx* ctx, uint32_t arity, uint32_t depth, const uint64_t* indices,
+                                const uint8_t* leaves, const uint8_t* paths, uint64_t n,
+                                uint8_t* roots) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (depth > 32) return INF_ERR_BAD_DEPTH;
+    if (n && (!indices || !leaves || !roots || (depth && !paths))) return INF_ERR_NULL_POINTER;
+    if (n == 0) return INF_OK;
+    Bind bind(ctx);
+    const size_t path_bytes = (size_t)n * depth * (arity - 1) * 32;
+    const size_t idx_bytes = (n * 8 + 31) & ~(size_t)31;          // keep the nodes 32-byte aligned
+    int rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], idx_bytes + n * 32 + path_bytes))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], n * 32))) return rc;
+    char* d_idx = (char*)ctx->io[0];
+    char* d_leaves = d_idx + idx_bytes;
+    char* d_paths = d_leaves + n * 32;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_idx, indices, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_leaves, leaves, n * 32, cudaMemcpyHostToDevice, st));
+    if (path_bytes) CU(cudaMemcpyAsync(d_paths, paths, path_bytes, cudaMemcpyHostToDevice, st));
+    CU(arity == 2 ? launch_path_root_t3(d_idx, d_leaves, d_paths, depth, ctx->io[1], n, st)
+                  : launch_path_root_t6(d_idx, d_leaves, d_paths, depth, ctx->io[1], n, st));
+    CU(cudaMemcpyAsync(roots, ctx->io[1], n * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return INF_OK;
 }
 

@@ -7,12 +7,16 @@
 #include <cstdint>
 #include <cstring>
 
-// 128 threads x 4 resident blocks = 16 warps/SM at <= 128 registers/thread.
+// 128-thread blocks.  Resident blocks per SM (register cap): measured on B200
+// (tools/variant_probe.py, profiles/r01_occupancy_sweep.md) — widths 2 and 3 fit
+// 94 registers and are indifferent; from width 4 on, 4 blocks (128 registers)
+// spill and 3 blocks (168 registers) are 5-21 % faster: the multiply pipe is the
+// bottleneck, 12 warps per SM already saturate it, spills only add traffic.
 #ifndef INF_BLOCK
 #define INF_BLOCK 128
 #endif
 #ifndef INF_MIN_BLOCKS
-#define INF_MIN_BLOCKS 4
+#define INF_MIN_BLOCKS(T) ((T) >= 4 ? 3 : 4)
 #endif
 
 namespace inf {
@@ -27,7 +31,9 @@ struct TagArg {          // domain tag in wire order (poseidon.rs:110-120); has 
     cudaError_t launch_hash_batch_t##N(const void* d_in, void* d_out, uint64_t n, const TagArg& tag, \
                                        bool le, cudaStream_t st);                                   \
     cudaError_t launch_tree_level_t##N(const void* d_in, uint64_t shift, uint64_t n_in, void* d_out, \
-                                       uint64_t n_out, const uint8_t* zero_be, cudaStream_t st);
+                                       uint64_t n_out, const uint8_t* zero_be, cudaStream_t st);    \
+    cudaError_t launch_path_root_t##N(const void* d_idx, const void* d_leaves, const void* d_paths,  \
+                                      uint32_t depth, void* d_roots, uint64_t n, cudaStream_t st);
 INF_DECLARE_WIDTH(2)
 INF_DECLARE_WIDTH(3)
 INF_DECLARE_WIDTH(4)
@@ -36,6 +42,20 @@ INF_DECLARE_WIDTH(6)
 INF_DECLARE_WIDTH(7)
 INF_DECLARE_WIDTH(8)
 #undef INF_DECLARE_WIDTH
+
+// Leaf hashing (leaves.cu)
+cudaError_t upload_leaf_tables(const uint32_t* t5, size_t w5, const uint32_t* t6, size_t w6);
+cudaError_t launch_interaction_leaves(const void* d_pk, const void* d_data, void* d_out, uint64_t n,
+                                      cudaStream_t st);
+cudaError_t launch_registration_leaves(const void* d_pk, const void* d_ts, void* d_out, uint64_t n,
+                                       cudaStream_t st);
+
+// Sibling-path gather over retained tree levels (tree_paths.cu)
+cudaError_t launch_gather_paths(const void* const* d_level_ptrs /* device array [depth] */,
+                                const uint64_t* d_level_counts /* device array [depth] */,
+                                const void* d_zero_nodes /* device, depth x 32 B */, uint32_t arity,
+                                uint32_t depth, const void* d_indices, uint64_t n, void* d_out,
+                                cudaStream_t st);
 
 // Generic dense kernel (any width 2..13), dense_generic.cu
 cudaError_t launch_hash_dense(int t, const uint32_t* d_tbl, const void* d_in, void* d_out,

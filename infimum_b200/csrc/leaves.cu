@@ -1,0 +1,104 @@
+// Leaf hashing: the step immediately before the trees.
+//
+//   registration leaf  = hash4(pk.x, pk.y, 1, timestamp)
+//        PollProvider::register_participant, pallet/src/poll/provider.rs:218-241
+//   interaction leaf   = hash4(hash5(d[0..5]), hash5(d[5..10]), pk.x, pk.y)
+//        PollProvider::consume_interaction,  pallet/src/poll/provider.rs:243-287
+//        (mirrors MessageHasher, circuits/utils/hashers.circom:39-78)
+//
+// One participant / one message per thread; the three hashes of a message are
+// fused in one kernel (2 x t=6 then t=5), intermediates never leave registers.
+// This translation unit owns its own copies of the t=5 and t=6 tables (22 KB +
+// 27 KB of the 64 KB constant bank).
+#include <cuda_runtime.h>
+
+#include "launch.h"
+#include "poseidon.cuh"
+
+namespace inf {
+namespace {
+
+__constant__ uint32_t c_tbl5[Layout<5>::WORDS];
+__constant__ uint32_t c_tbl6[Layout<6>::WORDS];
+
+__device__ __forceinline__ void load_node(uint32_t (&w)[8], const uint4* p) {
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// pk: n x (x, y) 32-byte big-endian; data: n x 10 x 32 bytes; out: n x 32 bytes
+__global__ void __launch_bounds__(INF_BLOCK, 3)
+interaction_leaf_kernel(const uint4* __restrict__ pk, const uint4* __restrict__ data,
+                        uint4* __restrict__ out, uint64_t n) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    uint32_t in4[4][8];
+    {
+        uint32_t half[5][8];
+        const uint4* d = data + idx * 20;
+#pragma unroll
+        for (int i = 0; i < 5; i++) load_node(half[i], d + 2 * i);
+        hash_words<6, false>(in4[0], half, nullptr, c_tbl6);          // hash5(d[0..5])
+#pragma unroll
+        for (int i = 0; i < 5; i++) load_node(half[i], d + 10 + 2 * i);
+        hash_words<6, false>(in4[1], half, nullptr, c_tbl6);          // hash5(d[5..10])
+    }
+    load_node(in4[2], pk + idx * 4);
+    load_node(in4[3], pk + idx * 4 + 2);
+    uint32_t leaf[8];
+    hash_words<5, false>(leaf, in4, nullptr, c_tbl5);                 // hash4(left, right, pk.x, pk.y)
+    store_node(out + 2 * idx, leaf);
+}
+
+// pk: n x (x, y); timestamps: n x u64 (block numbers); out: n x 32 bytes
+__global__ void __launch_bounds__(INF_BLOCK, 3)
+registration_leaf_kernel(const uint4* __restrict__ pk, const unsigned long long* __restrict__ ts,
+                         uint4* __restrict__ out, uint64_t n) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    uint32_t in4[4][8];
+    load_node(in4[0], pk + idx * 4);
+    load_node(in4[1], pk + idx * 4 + 2);
+    const unsigned long long t = ts[idx];
+#pragma unroll
+    for (int k = 0; k < 8; k++) in4[2][k] = in4[3][k] = 0;
+    in4[2][7] = 0x01000000u;                                           // Fr::from(1), big-endian bytes
+    in4[3][6] = bswap32((uint32_t)(t >> 32));                          // Fr::from(timestamp: u64)
+    in4[3][7] = bswap32((uint32_t)t);
+    uint32_t leaf[8];
+    hash_words<5, false>(leaf, in4, nullptr, c_tbl5);
+    store_node(out + 2 * idx, leaf);
+}
+
+}  // namespace
+
+cudaError_t upload_leaf_tables(const uint32_t* t5, size_t w5, const uint32_t* t6, size_t w6) {
+    if (w5 != (size_t)Layout<5>::WORDS || w6 != (size_t)Layout<6>::WORDS) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemcpyToSymbol(c_tbl5, t5, w5 * 4);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_tbl6, t6, w6 * 4);
+}
+
+cudaError_t launch_interaction_leaves(const void* d_pk, const void* d_data, void* d_out, uint64_t n,
+                                      cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    interaction_leaf_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_pk, (const uint4*)d_data, (uint4*)d_out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_registration_leaves(const void* d_pk, const void* d_ts, void* d_out, uint64_t n,
+                                       cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    registration_leaf_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_pk, (const unsigned long long*)d_ts,
+                                                       (uint4*)d_out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace inf

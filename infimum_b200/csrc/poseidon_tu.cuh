@@ -37,7 +37,7 @@ __device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
 }
 
 template <bool LE>
-__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS)
+__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
 hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_t n, TagArg tag) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
@@ -55,7 +55,7 @@ hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_
 // is the blank state leaf = zeroes[0] (state.rs:48-52), else 0.
 // out[i] = H(node[A*i], ..., node[A*i+A-1]); nodes past the end are the
 // level's zero value (PollStateTree::merge's right padding, state.rs:262-266).
-__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS)
+__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
 tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
                   uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     constexpr int A = T - 1;
@@ -75,6 +75,42 @@ tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
     }
     hash_words<T, false>(ow, iw, nullptr, c_tbl);
     store_node(out + 2 * idx, ow);
+}
+
+// Batched compute_merkle_root_from_path (pallet/src/poll/provider.rs:396-436):
+// one path per thread.  At every level the node sits at position idx % A among
+// its A-1 siblings (which are stored in order, skipping that position), the A
+// values are hashed, idx /= A.  paths: n x depth x (A-1) x 32 bytes.
+__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
+path_root_kernel(const uint64_t* __restrict__ indices, const uint4* __restrict__ leaves,
+                 const uint4* __restrict__ paths, uint32_t depth, uint4* __restrict__ roots,
+                 uint64_t n) {
+    constexpr int A = T - 1;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint64_t idx = indices[t];
+    uint32_t cur[8];
+    load_node(cur, leaves + 2 * t);
+    const uint4* p = paths + t * (uint64_t)depth * (A - 1) * 2;
+#pragma unroll 1
+    for (uint32_t l = 0; l < depth; l++) {
+        const uint32_t pos = (uint32_t)(idx % A);
+        uint32_t iw[A][8];
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            // sibling slot for position j: j-1 above the node, j below it; the
+            // slot read when j == pos is in range and discarded
+            int k = (uint32_t)j > pos ? j - 1 : j;
+            if (k > A - 2) k = A - 2;
+            uint32_t sib[8];
+            load_node(sib, p + ((uint64_t)l * (A - 1) + k) * 2);
+#pragma unroll
+            for (int w = 0; w < 8; w++) iw[j][w] = ((uint32_t)j == pos) ? cur[w] : sib[w];
+        }
+        hash_words<T, false>(cur, iw, nullptr, c_tbl);
+        idx /= A;
+    }
+    store_node(roots + 2 * t, cur);
 }
 
 }  // namespace
@@ -107,6 +143,16 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift
     memcpy(z.w, zero_be, 32);
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
     tree_level_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
+    return cudaGetLastError();
+}
+
+cudaError_t INF_CAT(launch_path_root_t, INF_T)(const void* d_idx, const void* d_leaves,
+                                               const void* d_paths, uint32_t depth, void* d_roots,
+                                               uint64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    path_root_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint64_t*)d_idx, (const uint4*)d_leaves,
+                                                 (const uint4*)d_paths, depth, (uint4*)d_roots, n);
     return cudaGetLastError();
 }
 

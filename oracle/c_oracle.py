@@ -73,3 +73,31 @@ def dense_tree_root(arity: int, depth: int, nodes, threads: int = 0, faithful: b
                                       threads or os.cpu_count() or 1, int(faithful))
     assert rc == 0
     return root.raw
+
+
+def registration_leaves(public_keys, timestamps, threads: int = 0) -> np.ndarray:
+    """hash4(pk.x, pk.y, 1, timestamp) per row (provider.rs:224-233)."""
+    pk = np.ascontiguousarray(np.frombuffer(public_keys, dtype=np.uint8) if not isinstance(public_keys, np.ndarray)
+                              else public_keys, dtype=np.uint8).reshape(-1, 64)
+    n = pk.shape[0]
+    rows = np.zeros((n, 4, 32), dtype=np.uint8)
+    rows[:, 0] = pk[:, :32]
+    rows[:, 1] = pk[:, 32:]
+    rows[:, 2, 31] = 1
+    ts = np.asarray(timestamps, dtype=np.uint64).reshape(-1)
+    rows[:, 3, 24:] = ts.astype(">u8").view(np.uint8).reshape(n, 8)
+    return hash_batch(4, rows, threads)
+
+
+def interaction_leaves(public_keys, data, threads: int = 0) -> np.ndarray:
+    """hash4(hash5(d[0..5]), hash5(d[5..10]), pk.x, pk.y) per row (provider.rs:249-278)."""
+    pk = np.ascontiguousarray(np.frombuffer(public_keys, dtype=np.uint8) if not isinstance(public_keys, np.ndarray)
+                              else public_keys, dtype=np.uint8).reshape(-1, 64)
+    d = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data,
+                             dtype=np.uint8).reshape(-1, 10, 32)
+    n = pk.shape[0]
+    left = hash_batch(5, np.ascontiguousarray(d[:, :5]), threads)
+    right = hash_batch(5, np.ascontiguousarray(d[:, 5:]), threads)
+    rows = np.empty((n, 4, 32), dtype=np.uint8)
+    rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3] = left, right, pk[:, :32], pk[:, 32:]
+    return hash_batch(4, rows, threads)

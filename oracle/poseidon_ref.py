@@ -413,3 +413,71 @@ def batch_merge(arity: int, full_depth: int, leaves: Sequence[bytes], *,
         while arity ** root_depth < n:
             root_depth += 1
     return dense_tree_root(lv, arity, root_depth), insert_depth, root_depth, count
+
+
+# ----------------------------------------------------------------------------
+# Merkle paths and outcome verification (provider.rs:76-139, 396-436)
+# ----------------------------------------------------------------------------
+def compute_merkle_root_from_path(depth: int, index: int, leaf: bytes, path, arity: int = 5):
+    """provider.rs:396-436 (the reference fixes arity 5, VOTE_TREE_ARITY): at
+    each level the node takes position index % arity among the arity-1 siblings
+    of path[level] (stored in order with that position skipped)."""
+    idx, cur = index, leaf
+    for i in range(depth):
+        pos = idx % arity
+        level = [cur if j == pos else path[i][j - 1 if j > pos else j] for j in range(arity)]
+        cur = hash_be(level)
+        idx //= arity
+    return cur
+
+
+def verify_outcome(vote_option_tree_depth: int, n_options: int, tally_commitment: bytes, outcome: dict):
+    """verify_outcome (provider.rs:76-139) minus the `is_proven` guard: every
+    option's tally result must hash, through its Merkle path and the two salts,
+    to the tally commitment; so must the total spent.  Returns the index of the
+    first option with the largest tally, or None."""
+    best, best_val = 0, 0
+    for i in range(n_options):
+        res = outcome["tally_results"][i]
+        root = compute_merkle_root_from_path(vote_option_tree_depth, i, res.to_bytes(32, "big"),
+                                             outcome["tally_result_proofs"][i])
+        h = hash_be([hash_be([root, outcome["tally_result_salt"]]), outcome["spent_votes_hash"]])
+        if h != tally_commitment:
+            return None
+        if res > best_val:
+            best, best_val = i, res
+    h = hash_be([outcome["new_results_commitment"], hash_be([outcome["total_spent"], outcome["total_spent_salt"]])])
+    if h != tally_commitment:
+        return None
+    return best
+
+
+def dense_tree_levels(leaves: Sequence[bytes], arity: int, depth: int):
+    """All levels (0 = leaves) of the dense zero-padded tree of `depth` levels."""
+    zeroes = merkle_zeroes(arity)
+    levels = [list(leaves)]
+    for l in range(depth):
+        cur, nxt = levels[-1], []
+        for i in range(0, len(cur), arity):
+            grp = cur[i:i + arity]
+            nxt.append(hash_be(grp + [zeroes[l]] * (arity - len(grp))))
+        levels.append(nxt)
+    return levels
+
+
+def merkle_path(levels, arity: int, index: int):
+    """Sibling path of leaf `index` in the layout compute_merkle_root_from_path
+    consumes; nodes to the right of a level's last node are its zero value."""
+    zeroes = merkle_zeroes(arity)
+    path, idx = [], index
+    for l in range(len(levels) - 1):
+        pos = idx % arity
+        base = idx - pos
+        sibs = []
+        for j in range(arity):
+            if j == pos:
+                continue
+            sibs.append(levels[l][base + j] if base + j < len(levels[l]) else zeroes[l])
+        path.append(sibs)
+        idx //= arity
+    return path

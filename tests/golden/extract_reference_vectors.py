@@ -118,6 +118,29 @@ def main():
             {"pk": {"x": a[12 * i], "y": a[12 * i + 1]}, "message": a[12 * i + 2:12 * i + 12]}
             for i in range(len(a) // 12)]
 
+    # ---- outcome fixtures (data.rs:223-275): pin compute_merkle_root_from_path and
+    # the tally-commitment hash chain of verify_outcome (provider.rs:76-139, 396-436).
+    # The last commitment of proof_batches is what commit_outcome leaves in
+    # commitment.tally.1 before verify_outcome runs (lib.rs:567-640).
+    for sid in (1, 2):
+        body = fn_body(da, "poll_scenario_%d" % sid)
+        batches = arrays32(body[body.index("proof_batches:"):body.index("expected:")])
+        out = body[body.index("outcome:"):]
+        fld = lambda k: arrays32(re.search(k + r":\s*\[[^\]]*\]", out).group(0))[0]
+        proofs = arrays32(out[out.index("tally_result_proofs:"):])
+        results = [int(x) for x in re.search(r"tally_results:\s*vec::Vec::from\(\[([^\]]*)\]\)", out).group(1).split(",") if x.strip()]
+        depth = v["poll_config"]["vote_option_tree_depth"]
+        assert len(proofs) == len(results) * depth * 4
+        v["scenario_%d_outcome" % sid] = {
+            "expected_outcome_index": int(re.search(r"expected:\s*Some\((\d+)\)", body).group(1)),
+            "final_tally_commitment": batches[-1], "batch_commitments": batches,
+            "tally_results": results,
+            "tally_result_proofs": [[proofs[(o * depth + l) * 4:(o * depth + l) * 4 + 4] for l in range(depth)]
+                                    for o in range(len(results))],
+            "total_spent": fld("total_spent"), "total_spent_salt": fld("total_spent_salt"),
+            "tally_result_salt": fld("tally_result_salt"), "new_results_commitment": fld("new_results_commitment"),
+            "spent_votes_hash": fld("spent_votes_hash")}
+
     # ---- tree pins (extrinsics.rs) -------------------------------------------
     a = arrays32(fn_body(ex, "merge_registration_state_success"))
     v["merge_registration_state_success"] = {

@@ -91,3 +91,15 @@ def test_insert_merge_equals_dense_tree(arity, full_depth, blank, to_depth):
             continue
         r2, idp, rdp, cnt = O.batch_merge(arity, full_depth, leaves, prepend_blank_leaf=blank, to_depth=to_depth)
         assert rc == 0 and root == r2 and depth == idp and count == cnt
+
+
+def test_leaf_helpers_match_python_oracle(golden):
+    p = golden["participant"]
+    pk = H(p["shared_pk"]["x"]) + H(p["shared_pk"]["y"])
+    msg = b"".join(H(x) for x in p["message"])
+    assert c_oracle.interaction_leaves(pk, msg)[0].tobytes() == \
+        O.interaction_leaf(H(p["shared_pk"]["x"]), H(p["shared_pk"]["y"]), [H(x) for x in p["message"]])
+    pks = b"".join(H(q["x"]) + H(q["y"]) for q in golden["participants"])
+    got = c_oracle.registration_leaves(pks, [2, 2, 2 ** 40 + 5])
+    for i, (q, ts) in enumerate(zip(golden["participants"], [2, 2, 2 ** 40 + 5])):
+        assert got[i].tobytes() == O.registration_leaf(H(q["x"]), H(q["y"]), ts)

@@ -357,3 +357,81 @@ def test_hypothesis_tree_and_reduction_properties(ib):
 
     reduction()
     tree()
+
+
+# ---- leaf hashing (provider.rs:218-287) ------------------------------------------------------------
+def test_leaf_hashing_pins_and_oracle(ib, golden):
+    """The reference pins leaf hashing only through the tree roots: rebuild both
+    pinned trees from raw keys / messages with the fused leaf kernels."""
+    cfg = golden["poll_config"]
+    poll = ib.Poll(ib.PollConfig(cfg["registration_depth"], cfg["interaction_depth"],
+                                 cfg["process_subtree_depth"], cfg["tally_subtree_depth"]))
+    blk = golden["merge_registration_state_success"]["registration_block"]
+    for i, q in enumerate(golden["participants"]):
+        assert poll.register_participant((H(q["x"]), H(q["y"])), blk) == i + 1
+    poll.merge_registrations()
+    assert poll.registrations.root == H(golden["merge_registration_state_success"]["registrations_root"])
+    assert poll.commitment.process == (0, H(golden["merge_registration_state_success"]["process_commitment"]))
+    assert poll.registrations.depth == golden["process_messages_public_signals"]["registrations_depth"]
+    p = golden["participant"]
+    assert poll.consume_interaction((H(p["shared_pk"]["x"]), H(p["shared_pk"]["y"])), [H(x) for x in p["message"]]) == 1
+    poll.merge_interactions()
+    assert poll.interactions.root == H(golden["merge_interaction_state_success"]["interactions_root"])
+    assert (poll.commitment.expected_process, poll.commitment.expected_tally) == \
+        (golden["merge_interaction_state_success"]["expected_process"], golden["merge_interaction_state_success"]["expected_tally"])
+
+
+def test_leaf_hashing_batches_vs_oracle(ib):
+    n = 20000
+    pk = random_fr_bytes(2 * n, seed=61, canonical=False).reshape(n, 64)
+    data = random_fr_bytes(10 * n, seed=62, canonical=False).reshape(n, 320)
+    ts = np.random.default_rng(63).integers(0, 2 ** 63, size=n, dtype=np.uint64)
+    ts[:4] = [0, 1, 2 ** 32 - 1, 2 ** 64 - 1]
+    assert (ib.interaction_leaves(pk, data) == c_oracle.interaction_leaves(pk, data)).all()
+    assert (ib.registration_leaves(pk, ts) == c_oracle.registration_leaves(pk, ts)).all()
+    # ragged tail of the chunked pipeline
+    m = (1 << 17) + 77
+    pk = random_fr_bytes(2 * m, seed=64).reshape(m, 64)
+    ts = np.arange(m, dtype=np.uint64)
+    got = ib.registration_leaves(pk, ts)
+    idx = np.r_[0:50, (1 << 17) - 25:(1 << 17) + 77]
+    assert (got[idx] == c_oracle.registration_leaves(pk[idx], ts[idx])).all()
+
+
+# ---- Merkle paths and verify_outcome (provider.rs:76-139, 396-436) ---------------------------------
+@pytest.mark.parametrize("sid", [1, 2])
+def test_verify_outcome_scenarios(ib, golden, sid):
+    o = golden["scenario_%d_outcome" % sid]
+    outcome = {k: H(o[k]) for k in ("total_spent", "total_spent_salt", "tally_result_salt",
+                                    "new_results_commitment", "spent_votes_hash")}
+    outcome["tally_results"] = o["tally_results"]
+    outcome["tally_result_proofs"] = [[[H(x) for x in lvl] for lvl in opt] for opt in o["tally_result_proofs"]]
+    depth = golden["poll_config"]["vote_option_tree_depth"]
+    commitment = H(o["final_tally_commitment"])
+    assert ib.verify_outcome(depth, 25, commitment, outcome) == o["expected_outcome_index"]
+    assert ib.verify_outcome(depth, 25, commitment, dict(outcome, spent_votes_hash=bytes(32))) is None
+    for i in (0, 5, 23, 24):
+        got = ib.compute_merkle_root_from_path(depth, i, be(o["tally_results"][i]), outcome["tally_result_proofs"][i])
+        assert got == O.compute_merkle_root_from_path(depth, i, be(o["tally_results"][i]), outcome["tally_result_proofs"][i])
+
+
+@pytest.mark.parametrize("arity,depth,blank,n", [(5, 4, False, 611), (2, 10, True, 1000), (2, 9, False, 512), (5, 3, False, 1)])
+def test_retained_tree_paths(ib, arity, depth, blank, n):
+    leaves = random_fr_bytes(n, seed=arity * 7 + depth)
+    tree = ib.RetainedTree(arity, depth, leaves, prepend_blank_leaf=blank)
+    logical = ([ib.get_merkle_zeroes(arity)[0]] if blank else []) + [leaves[i].tobytes() for i in range(n)]
+    levels = O.dense_tree_levels(logical, arity, depth) if n <= 1000 else None
+    assert tree.root == levels[-1][0]
+    rc, root, _, _ = c_oracle.tree_insert_merge(arity, depth, blank, True, leaves)
+    assert tree.root == root
+    rng = np.random.default_rng(5)
+    idx = np.unique(np.r_[0, len(logical) - 1, rng.integers(0, len(logical), size=40)]).astype(np.uint64)
+    paths = tree.paths(idx)
+    for k, i in enumerate(idx):
+        exp = O.merkle_path(levels, arity, int(i))
+        got = [[paths[k, l, s].tobytes() for s in range(arity - 1)] for l in range(depth)]
+        assert got == exp, (arity, int(i))
+    # and the batched verifier closes the loop on the device
+    roots = ib.merkle_roots_from_paths(arity, depth, idx, np.stack([np.frombuffer(logical[int(i)], dtype=np.uint8) for i in idx]), paths)
+    assert all(roots[k].tobytes() == tree.root for k in range(len(idx)))
+    tree.close()

@@ -175,3 +175,35 @@ def test_batch_equivalence(arity, full_depth, to_depth, blank):
         assert t.root == root, (arity, n)
         assert depth_after_insert == insert_depth, (arity, n)
         assert t.count == count
+
+
+def _outcome(golden, sid):
+    o = golden["scenario_%d_outcome" % sid]
+    out = {k: H(o[k]) for k in ("total_spent", "total_spent_salt", "tally_result_salt", "new_results_commitment",
+                               "spent_votes_hash")}
+    out["tally_results"] = o["tally_results"]
+    out["tally_result_proofs"] = [[[H(x) for x in lvl] for lvl in opt] for opt in o["tally_result_proofs"]]
+    return out, H(o["final_tally_commitment"]), o["expected_outcome_index"]
+
+
+@pytest.mark.parametrize("sid", [1, 2])
+def test_verify_outcome_scenarios(golden, sid):
+    """data.rs:241-275: the circuits' own tally proofs and salts must hash to the
+    final tally commitment through compute_merkle_root_from_path (hash5 paths)
+    and the hash2 chain of verify_outcome; expected winners 5 and 23."""
+    outcome, commitment, expected = _outcome(golden, sid)
+    depth = golden["poll_config"]["vote_option_tree_depth"]
+    assert O.verify_outcome(depth, 25, commitment, outcome) == expected
+    bad = dict(outcome, tally_result_salt=bytes(32))
+    assert O.verify_outcome(depth, 25, commitment, bad) is None
+
+
+def test_merkle_path_roundtrip():
+    leaves = [be(1000 + i) for i in range(38)]
+    for arity, depth in ((5, 3), (2, 6)):
+        levels = O.dense_tree_levels(leaves, arity, depth)
+        root = levels[-1][0]
+        assert root == O.dense_tree_root(leaves, arity, depth)
+        for idx in (0, 1, 4, 5, 24, 37):
+            path = O.merkle_path(levels, arity, idx)
+            assert O.compute_merkle_root_from_path(depth, idx, leaves[idx], path, arity) == root
