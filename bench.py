@@ -46,6 +46,9 @@ IMAD_PER_CLK_PER_SM = 64            # CUDA programming guide, 32-bit integer mul
 METRIC = "Poseidon-BN254 hashes/s"
 
 
+_emit = print
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -289,6 +292,9 @@ def run_ours(args, rank, world, local_rank):
     e2e_ok = bool((h_out_np[:: n // 64][:64].copy() == d_out[:: n // 64][:64].cpu().numpy()).all())
     del h_in, h_out
 
+    props = torch.cuda.get_device_properties(dev)
+    sms_peak = props.multi_processor_count * IMAD_PER_CLK_PER_SM * 1965.0e6 / 1e12
+
     # ---- tree merge of the 2^24-leaf poll tree, sharded over the ranks ----------------------
     n_leaves = 1 << args.log_leaves
     plan = sharded.make_plan(2, args.log_leaves, n_leaves, prepend_blank_leaf=False, to_depth=True, world=world)
@@ -313,6 +319,78 @@ def run_ours(args, rank, world, local_rank):
     tree_best = min(tree_ms)
     n_tree_hashes = n_leaves - 1
     root_hex = bytes(root.cpu().numpy().tobytes()).hex()
+
+    # ---- the other BASELINE configs and the "next" rows, rank 0 only, short ---------------------
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        del leaves
+        torch.cuda.empty_cache()
+        W_HASH5, W_HASH4 = 731808, 528000
+
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize(dev)
+            best = None
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    fn()
+                    e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            return best
+
+        def merge_dev_ms(arity, full_depth, lv, blank, to_depth):
+            root = C.create_string_buffer(32)
+            idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
+
+            def run():
+                rc = ctx.lib.inf_tree_merge_dev(ctx.handle, arity, full_depth, int(blank), int(to_depth), lv.data_ptr(),
+                                                lv.shape[0], root, C.byref(idp), C.byref(rdp), C.byref(has),
+                                                stream.cuda_stream)
+                assert rc in (0, 2), rc
+            return timed(run), root.raw.hex(), idp.value, rdp.value
+
+        # configs[2]: state-tree merge of 2^20 registrations (+ blank leaf): depth field 20, root depth 21
+        lv = device_random_fr(1 << 20, dev, seed=20)
+        ms, root_hex2, idp, rdp = merge_dev_ms(2, 32, lv, True, False)
+        nh = (1 << 20) + 20            # 2^20 + 20 parents for 2^20 + 1 logical leaves
+        extras["state_tree_2^20"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
+                                     "root_depth": rdp, "roofline_frac": nh * W_HASH2 / (ms * 1e-3) / 1e12 / (sms_peak),
+                                     "root": root_hex2}
+        # configs[3] on one GPU: message-tree merge of 2^26 interaction leaves, arity 5, depth 12
+        lv = device_random_fr(1 << 26, dev, seed=26)
+        ms, root_hex5, idp, rdp = merge_dev_ms(5, 12, lv, False, True)
+        nh, c = 0, 1 << 26
+        for _ in range(12):
+            c = -(-c // 5)
+            nh += c
+        extras["message_tree_2^26"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
+                                       "root_depth": rdp, "roofline_frac": nh * W_HASH5 / (ms * 1e-3) / 1e12 / (sms_peak),
+                                       "root": root_hex5}
+        # hash5 batch (t = 6), 2^22 tuples
+        n5 = 1 << 22
+        d5 = lv[: 5 * n5]
+        o5 = torch.empty((n5, 32), dtype=torch.uint8, device=dev)
+        h5 = ib.Poseidon.new_circom(5, ctx)
+        ms = timed(lambda: h5.hash_batch_device(d5.data_ptr(), n5, o5.data_ptr(), stream.cuda_stream))
+        extras["hash5_2^22"] = {"ms": ms, "hashes_per_s": n5 / (ms * 1e-3),
+                                "roofline_frac": n5 * W_HASH5 / (ms * 1e-3) / 1e12 / sms_peak}
+        # next row: fused interaction-leaf hashing, 2^20 messages (2 x hash5 + hash4 each)
+        nm = 1 << 20
+        pk, dat = lv[: 2 * nm], lv[2 * nm: 12 * nm]
+        ol = torch.empty((nm, 32), dtype=torch.uint8, device=dev)
+
+        def leaf_run():
+            rc = ctx.lib.inf_interaction_leaves_dev(ctx.handle, pk.data_ptr(), dat.data_ptr(), nm, ol.data_ptr(),
+                                                    stream.cuda_stream)
+            assert rc == 0
+        ms = timed(leaf_run)
+        extras["interaction_leaves_2^20"] = {"ms": ms, "messages_per_s": nm / (ms * 1e-3),
+                                             "roofline_frac": nm * (2 * W_HASH5 + W_HASH4) / (ms * 1e-3) / 1e12 / sms_peak}
+        del lv, d5, o5, pk, dat, ol
 
     if rank != 0:
         return 0
@@ -383,10 +461,11 @@ def run_ours(args, rank, world, local_rank):
                        "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / (peak * world),
                        "root": root_hex},
         "bit_exact_sample": ok,
+        "other_configs": extras,
     }
     if base:
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
 
 
@@ -399,6 +478,7 @@ def main():
     ap.add_argument("--log-pairs", type=int, default=LOG_PAIRS)
     ap.add_argument("--log-leaves", type=int, default=LOG_LEAVES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs / next-row timings")
     args = ap.parse_args()
 
     world = _env_int("WORLD_SIZE", 1)
@@ -412,6 +492,15 @@ def main():
         return subprocess.call(cmd)
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # Libraries (NCCL's version banner, torchrun) may write to stdout; the contract
+    # is ONE JSON line there, so everything else goes to stderr for the duration.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())
     rc = run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist

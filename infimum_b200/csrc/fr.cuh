@@ -117,6 +117,10 @@ INF_HD void chain4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint3
 //   (r1:r0) += p1*m + carry ; (r3:r2) += p3*m ; (r5:r4) += p5*m ; (r7:r6) += p7*m
 //   top    += final carry
 // i.e. the odd-limb half of "+= m*p".  Returns m.  mul.lo leaves CC alone.
+// (m and the p0 row CAN be formed with shifts and adds, since p0 = 2^32-2^28+1
+// and -p^-1 = -(2^28+1); measured on B200 that is 11 % SLOWER — the extra ALU
+// instructions cost more issue time than the IMAD + IMAD.HI they replace,
+// profiles/r01_alu_reduction_experiment.md — so the multiplies stay.)
 INF_HD uint32_t chain4_fold_reduce(uint32_t& m_col, uint32_t s_col, uint32_t& r0, uint32_t& r1,
                                    uint32_t& r2, uint32_t& r3, uint32_t& r4, uint32_t& r5,
                                    uint32_t& r6, uint32_t& r7, uint32_t& top) {
