@@ -434,4 +434,206 @@ merge_interactions(PollStateTree interactions, uint32_t registrations_count, uin
     return std::make_pair(std::move(t), commitment);
 }
 
+
+// ---- keys and leaf hashing (keys.rs, provider.rs:218-287) -------------------------------------------
+struct PublicKey {                                       // keys.rs: PublicKey { x, y }
+    HashBytes x{}, y{};
+};
+using PollInteractionData = std::array<HashBytes, 10>;   // poll.rs
+
+// Bulk forms of the leaf computations, one participant / message per GPU thread.
+inline Result<std::vector<HashBytes>, MerkleTreeError>
+registration_leaves(const std::vector<PublicKey>& keys, const std::vector<uint64_t>& timestamps, Context* ctx = nullptr) {
+    if (keys.size() != timestamps.size()) return MerkleTreeError::HashFailed;
+    std::vector<HashBytes> out(keys.size());
+    static_assert(sizeof(PublicKey) == 64, "PublicKey must be two packed 32-byte coordinates");
+    int rc = inf_registration_leaves((ctx ? ctx : &Context::global())->get(),
+                                     keys.empty() ? nullptr : keys[0].x.data(), timestamps.data(), keys.size(),
+                                     out.empty() ? nullptr : out[0].data());
+    if (rc) return MerkleTreeError::HashFailed;
+    return out;
+}
+inline Result<std::vector<HashBytes>, MerkleTreeError>
+interaction_leaves(const std::vector<PublicKey>& keys, const std::vector<PollInteractionData>& data, Context* ctx = nullptr) {
+    if (keys.size() != data.size()) return MerkleTreeError::HashFailed;
+    std::vector<HashBytes> out(keys.size());
+    int rc = inf_interaction_leaves((ctx ? ctx : &Context::global())->get(),
+                                    keys.empty() ? nullptr : keys[0].x.data(),
+                                    data.empty() ? nullptr : data[0][0].data(), keys.size(),
+                                    out.empty() ? nullptr : out[0].data());
+    if (rc) return MerkleTreeError::HashFailed;
+    return out;
+}
+
+// The slice of `Poll` that drives the hot path: the two trees, the commitment,
+// and register_participant / consume_interaction / merge_* with the reference's
+// signatures (provider.rs:218-327).  Leaves are hashed in bulk at merge time.
+struct Poll {
+    PollStateTree registrations, interactions;
+    Commitment commitment;
+    uint8_t process_subtree_depth = 0, tally_subtree_depth = 0;
+
+    Poll(uint8_t registration_depth, uint8_t interaction_depth, uint8_t process_subtree_depth_,
+         uint8_t tally_subtree_depth_, Context* ctx = nullptr)
+        : registrations(new_registration_tree(registration_depth, ctx)),
+          interactions(new_interaction_tree(interaction_depth, ctx)),
+          process_subtree_depth(process_subtree_depth_), tally_subtree_depth(tally_subtree_depth_), ctx_(ctx) {}
+
+    Result<uint32_t, MerkleTreeError> register_participant(const PublicKey& pk, uint64_t timestamp) {
+        if (registrations.root) return MerkleTreeError::TreeAlreadyFull;
+        reg_keys_.push_back(pk);
+        reg_ts_.push_back(timestamp);
+        return registrations.count + (uint32_t)reg_keys_.size();
+    }
+    Result<uint32_t, MerkleTreeError> consume_interaction(const PublicKey& pk, const PollInteractionData& data) {
+        if (interactions.root) return MerkleTreeError::TreeAlreadyFull;
+        msg_keys_.push_back(pk);
+        msg_data_.push_back(data);
+        return interactions.count + (uint32_t)msg_keys_.size();
+    }
+    std::optional<MerkleTreeError> merge_registrations() {
+        if (auto e = flush()) return e;
+        auto r = infimum::merge_registrations(std::move(registrations), commitment);
+        if (r.is_err()) return r.unwrap_err();
+        registrations = std::move(r.unwrap().first);
+        commitment = r.unwrap().second;
+        return std::nullopt;
+    }
+    std::optional<MerkleTreeError> merge_interactions() {
+        if (auto e = flush()) return e;
+        auto r = infimum::merge_interactions(std::move(interactions), registrations.count, process_subtree_depth,
+                                             tally_subtree_depth, commitment);
+        if (r.is_err()) return r.unwrap_err();
+        interactions = std::move(r.unwrap().first);
+        commitment = r.unwrap().second;
+        return std::nullopt;
+    }
+
+private:
+    Context* ctx_;
+    std::vector<PublicKey> reg_keys_, msg_keys_;
+    std::vector<uint64_t> reg_ts_;
+    std::vector<PollInteractionData> msg_data_;
+    std::optional<MerkleTreeError> flush() {
+        if (!reg_keys_.empty()) {
+            auto lv = registration_leaves(reg_keys_, reg_ts_, ctx_);
+            if (lv.is_err()) return lv.unwrap_err();
+            auto t = std::move(registrations).extend(lv.unwrap()[0].data(), lv.unwrap().size());
+            if (t.is_err()) return t.unwrap_err();
+            registrations = std::move(t.unwrap());
+            reg_keys_.clear(); reg_ts_.clear();
+        }
+        if (!msg_keys_.empty()) {
+            auto lv = interaction_leaves(msg_keys_, msg_data_, ctx_);
+            if (lv.is_err()) return lv.unwrap_err();
+            auto t = std::move(interactions).extend(lv.unwrap()[0].data(), lv.unwrap().size());
+            if (t.is_err()) return t.unwrap_err();
+            interactions = std::move(t.unwrap());
+            msg_keys_.clear(); msg_data_.clear();
+        }
+        return std::nullopt;
+    }
+};
+
+// ---- Merkle paths and outcome verification (provider.rs:76-139, 396-436) ------------------------------
+using MerklePath = std::vector<std::vector<HashBytes>>;     // [level][arity-1 siblings]
+
+// compute_merkle_root_from_path (arity 5, VOTE_TREE_ARITY)
+inline std::optional<HashBytes> compute_merkle_root_from_path(uint8_t depth, uint32_t index, const HashBytes& leaf,
+                                                              const MerklePath& path, Context* ctx = nullptr) {
+    if (path.size() < depth) return std::nullopt;
+    std::vector<uint8_t> flat;
+    for (uint8_t l = 0; l < depth; l++) {
+        if (path[l].size() < 4) return std::nullopt;
+        for (int k = 0; k < 4; k++) flat.insert(flat.end(), path[l][k].begin(), path[l][k].end());
+    }
+    uint64_t idx = index;
+    HashBytes root;
+    int rc = inf_merkle_roots_from_paths((ctx ? ctx : &Context::global())->get(), 5, depth, &idx, leaf.data(),
+                                         flat.data(), 1, root.data());
+    if (rc) return std::nullopt;
+    return root;
+}
+
+struct PollOutcome {                                        // coordinator.rs:53-77
+    std::vector<uint32_t> tally_results;
+    std::vector<MerklePath> tally_result_proofs;
+    HashBytes total_spent{}, total_spent_salt{}, tally_result_salt{}, new_results_commitment{}, spent_votes_hash{};
+};
+
+// verify_outcome without the `is_proven` guard; the per-option work is batched
+// (one path-root launch over all vote options, then two hash2 batches).
+inline std::optional<uint32_t> verify_outcome(uint8_t vote_option_tree_depth, size_t n_options,
+                                              const HashBytes& tally_commitment, const PollOutcome& o,
+                                              Context* ctx = nullptr) {
+    Context* c = ctx ? ctx : &Context::global();
+    if (o.tally_results.size() < n_options || o.tally_result_proofs.size() < n_options) return std::nullopt;
+    const uint8_t d = vote_option_tree_depth;
+    std::vector<uint64_t> idx(n_options);
+    std::vector<uint8_t> leaves(32 * n_options, 0), flat;
+    for (size_t i = 0; i < n_options; i++) {
+        idx[i] = i;
+        const uint32_t r = o.tally_results[i];
+        for (int b = 0; b < 4; b++) leaves[32 * i + 28 + b] = (uint8_t)(r >> (24 - 8 * b));
+        if (o.tally_result_proofs[i].size() < d) return std::nullopt;
+        for (uint8_t l = 0; l < d; l++) {
+            if (o.tally_result_proofs[i][l].size() < 4) return std::nullopt;
+            for (int k = 0; k < 4; k++)
+                flat.insert(flat.end(), o.tally_result_proofs[i][l][k].begin(), o.tally_result_proofs[i][l][k].end());
+        }
+    }
+    std::vector<HashBytes> roots(n_options);
+    if (inf_merkle_roots_from_paths(c->get(), 5, d, idx.data(), leaves.data(), flat.data(), n_options, roots[0].data()))
+        return std::nullopt;
+    auto h2 = Poseidon::new_circom(2, c).unwrap();
+    std::vector<uint8_t> rows(64 * n_options);
+    for (size_t i = 0; i < n_options; i++) {
+        memcpy(&rows[64 * i], roots[i].data(), 32);
+        memcpy(&rows[64 * i + 32], o.tally_result_salt.data(), 32);
+    }
+    auto a = h2.hash_batch(rows.data(), n_options);
+    if (a.is_err()) return std::nullopt;
+    for (size_t i = 0; i < n_options; i++) {
+        memcpy(&rows[64 * i], a.unwrap()[i].data(), 32);
+        memcpy(&rows[64 * i + 32], o.spent_votes_hash.data(), 32);
+    }
+    auto b = h2.hash_batch(rows.data(), n_options);
+    if (b.is_err()) return std::nullopt;
+    for (size_t i = 0; i < n_options; i++)
+        if (b.unwrap()[i] != tally_commitment) return std::nullopt;
+    auto t1 = PollStateTree::hash({o.total_spent, o.total_spent_salt}, c);
+    if (t1.is_err()) return std::nullopt;
+    auto t2 = PollStateTree::hash({o.new_results_commitment, t1.unwrap()}, c);
+    if (t2.is_err() || t2.unwrap() != tally_commitment) return std::nullopt;
+    uint32_t best = 0, best_val = 0;
+    for (size_t i = 0; i < n_options; i++)
+        if (o.tally_results[i] > best_val) { best = (uint32_t)i; best_val = o.tally_results[i]; }
+    return best;
+}
+
+// ---- retained tree: every level on the device, bulk sibling paths ----------------------------------------
+class RetainedTree {
+    inf_tree* t_ = nullptr;
+    uint32_t arity_, depth_;
+public:
+    RetainedTree(uint8_t arity, uint8_t depth, const uint8_t* leaves, uint64_t n, bool prepend_blank_leaf = false,
+                 Context* ctx = nullptr) : arity_(arity), depth_(depth) {
+        int rc = inf_tree_build((ctx ? ctx : &Context::global())->get(), arity, depth, prepend_blank_leaf, leaves, n, &t_);
+        if (rc) throw std::runtime_error(std::string("inf_tree_build: ") + inf_strerror(rc));
+    }
+    ~RetainedTree() { inf_tree_destroy(t_); }
+    RetainedTree(const RetainedTree&) = delete;
+    RetainedTree& operator=(const RetainedTree&) = delete;
+    HashBytes root() const { HashBytes r; inf_tree_root(t_, r.data()); return r; }
+    std::vector<MerklePath> paths(const std::vector<uint64_t>& leaf_indices) const {
+        std::vector<uint8_t> flat(leaf_indices.size() * depth_ * (arity_ - 1) * 32);
+        int rc = inf_tree_paths(t_, leaf_indices.data(), leaf_indices.size(), flat.data());
+        if (rc) throw std::runtime_error(std::string("inf_tree_paths: ") + inf_strerror(rc));
+        std::vector<MerklePath> out(leaf_indices.size(), MerklePath(depth_, std::vector<HashBytes>(arity_ - 1)));
+        size_t k = 0;
+        for (auto& p : out) for (auto& lvl : p) for (auto& h : lvl) { memcpy(h.data(), &flat[32 * k++], 32); }
+        return out;
+    }
+};
+
 }  // namespace infimum

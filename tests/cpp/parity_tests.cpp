@@ -7,11 +7,13 @@
 // plus oracle parity for ragged trees and the frontier.  Golden values come
 // from tests/golden/reference_vectors.json via the generated golden_vectors.h.
 // The oracle (liboracle.so) is linked as the checker only.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <random>
 #include <string>
+#include <tuple>
 
 #include "golden_vectors.h"
 #include "infimum_b200.hpp"
@@ -226,6 +228,64 @@ static void tree_and_frontier_vs_oracle() {
     }
 }
 
+// ---- leaf hashing through the Poll mirror (provider.rs:218-287) -----------------------------------
+static void poll_register_interact_merge() {
+    Poll poll(G_REGISTRATION_DEPTH, G_INTERACTION_DEPTH, G_PROCESS_SUBTREE_DEPTH, G_TALLY_SUBTREE_DEPTH);
+    for (int i = 0; i < 3; i++) {
+        PublicKey pk{HB(G_PARTICIPANTS[i][0]), HB(G_PARTICIPANTS[i][1])};
+        CHECK(poll.register_participant(pk, G_REGISTRATION_BLOCK).unwrap() == (uint32_t)(i + 1));
+    }
+    CHECK(!poll.merge_registrations().has_value());
+    CHECK(poll.registrations.root == std::optional<HashBytes>(HB(G_REGISTRATIONS_ROOT)));
+    CHECK(poll.commitment.process == std::make_pair(0u, HB(G_PROCESS_COMMITMENT)));
+    CHECK(poll.registrations.depth == G_REGISTRATIONS_DEPTH);
+    PollInteractionData data;
+    for (int i = 0; i < 10; i++) data[i] = HB(G_MESSAGE[i]);
+    CHECK(poll.consume_interaction(PublicKey{HB(G_SHARED_PK[0]), HB(G_SHARED_PK[1])}, data).unwrap() == 1);
+    CHECK(!poll.merge_interactions().has_value());
+    CHECK(poll.interactions.root == std::optional<HashBytes>(HB(G_INTERACTIONS_ROOT)));
+    CHECK(poll.commitment.expected_process == G_EXPECTED_PROCESS && poll.commitment.expected_tally == G_EXPECTED_TALLY);
+}
+
+// ---- verify_outcome against the reference's scenario fixtures (data.rs:241-275) ---------------------
+static void verify_outcome_scenarios() {
+    for (int sid = 0; sid < 2; sid++) {
+        PollOutcome o;
+        for (int i = 0; i < 25; i++) {
+            o.tally_results.push_back(G_OUTCOME_TALLY_RESULTS[sid][i]);
+            MerklePath p(2, std::vector<HashBytes>(4));
+            for (int l = 0; l < 2; l++) for (int k = 0; k < 4; k++) p[l][k] = HB(G_OUTCOME_PROOFS[sid][i][l][k]);
+            o.tally_result_proofs.push_back(p);
+        }
+        o.total_spent = HB(G_OUTCOME_FIELDS[sid][0]); o.total_spent_salt = HB(G_OUTCOME_FIELDS[sid][1]);
+        o.tally_result_salt = HB(G_OUTCOME_FIELDS[sid][2]); o.new_results_commitment = HB(G_OUTCOME_FIELDS[sid][3]);
+        o.spent_votes_hash = HB(G_OUTCOME_FIELDS[sid][4]);
+        const HashBytes commitment = HB(G_OUTCOME_FIELDS[sid][5]);
+        CHECK(verify_outcome(2, 25, commitment, o) == std::optional<uint32_t>(G_OUTCOME_EXPECTED[sid]));
+        PollOutcome bad = o;
+        bad.tally_result_salt[31] ^= 1;
+        CHECK(!verify_outcome(2, 25, commitment, bad).has_value());
+    }
+}
+
+// ---- retained tree + paths round trip ------------------------------------------------------------------
+static void retained_tree_paths() {
+    std::mt19937_64 rng(7);
+    std::vector<uint8_t> leaves(32 * 611);
+    for (auto& b : leaves) b = (uint8_t)rng();
+    RetainedTree tree(5, 4, leaves.data(), 611);
+    uint8_t exp[32];
+    uint32_t st[3];
+    oracle_tree_insert_merge(5, 4, 0, 1, leaves.data(), 611, exp, st, 0);
+    CHECK(tree.root() == HB(exp));
+    std::vector<uint64_t> idx = {0, 1, 4, 5, 124, 125, 300, 610};
+    auto paths = tree.paths(idx);
+    for (size_t k = 0; k < idx.size(); k++) {
+        auto r = compute_merkle_root_from_path(4, (uint32_t)idx[k], HB(&leaves[32 * idx[k]]), paths[k]);
+        CHECK(r == std::optional<HashBytes>(tree.root()));
+    }
+}
+
 int main() {
     struct T { const char* name; std::function<void()> fn; };
     const T tests[] = {
@@ -237,6 +297,9 @@ int main() {
         {"process_messages_public_signals", process_messages_public_signals},
         {"participant_limit_reached", participant_limit_reached},
         {"tree_and_frontier_vs_oracle", tree_and_frontier_vs_oracle},
+        {"poll_register_interact_merge", poll_register_interact_merge},
+        {"verify_outcome_scenarios", verify_outcome_scenarios},
+        {"retained_tree_paths", retained_tree_paths},
     };
     for (const T& t : tests) {
         int before = g_failed;

@@ -56,6 +56,18 @@ def _write_golden_header(path):
         g["merge_interaction_state_success"]["expected_process"], g["merge_interaction_state_success"]["expected_tally"],
         g["process_messages_public_signals"]["registrations_depth"]))
     L.append('static const char* G_COORD_PUB_KEY_HASH_DECIMAL = "%s";' % g["process_messages_public_signals"]["coord_pub_key_hash_decimal"])
+    sc = [g["scenario_1_outcome"], g["scenario_2_outcome"]]
+    L.append("static const uint32_t G_OUTCOME_TALLY_RESULTS[2][25] = {%s};" % ", ".join(
+        "{%s}" % ", ".join(str(x) for x in o["tally_results"]) for o in sc))
+    L.append("static const uint32_t G_OUTCOME_EXPECTED[2] = {%d, %d};" % tuple(o["expected_outcome_index"] for o in sc))
+    bb = lambda h: "{%s}" % ", ".join(str(x) for x in bytes.fromhex(h))
+    L.append("static const uint8_t G_OUTCOME_FIELDS[2][6][32] = {%s};" % ", ".join(
+        "{%s}" % ", ".join(bb(o[k]) for k in ("total_spent", "total_spent_salt", "tally_result_salt",
+                                              "new_results_commitment", "spent_votes_hash", "final_tally_commitment"))
+        for o in sc))
+    L.append("static const uint8_t G_OUTCOME_PROOFS[2][25][2][4][32] = {%s};" % ", ".join(
+        "{%s}" % ", ".join("{%s}" % ", ".join("{%s}" % ", ".join(bb(x) for x in lvl) for lvl in opt)
+                           for opt in o["tally_result_proofs"]) for o in sc))
     os.makedirs(os.path.dirname(path), exist_ok=True)
     open(path, "w").write("\n".join(L) + "\n")
 
