@@ -320,6 +320,43 @@ def run_ours(args, rank, world, local_rank):
     n_tree_hashes = n_leaves - 1
     root_hex = bytes(root.cpu().numpy().tobytes()).hex()
 
+    # ---- BASELINE configs[3] / [2] sharded the same way when there is more than one rank ---------
+    sharded_extras = {}
+    if world > 1 and not args.no_extras:
+        del leaves
+        torch.cuda.empty_cache()
+
+        def sharded_ms(arity, full_depth, n_lv, blank, to_depth, seed):
+            pl = sharded.make_plan(arity, full_depth, n_lv, prepend_blank_leaf=blank, to_depth=to_depth, world=world)
+            a, b = pl.leaf_range(rank)
+            lv = device_random_fr_range(a, b, dev, seed=seed)
+            best, r = None, None
+            for it in range(3):
+                barrier()
+                with torch.cuda.stream(stream):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    r = sharded.sharded_tree_merge(lv, pl, backend)
+                    e1.record(stream)
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if it >= 1:
+                    best = float(t.item()) if best is None else min(best, float(t.item()))
+            return best, r.cpu().numpy().tobytes().hex(), pl
+
+        ms, rh, pl = sharded_ms(5, 12, 1 << 26, False, True, 26)
+        sharded_extras["message_tree_2^26_sharded"] = {
+            "ms": ms, "n_gpus": world, "hashes": 16777220, "hashes_per_s": 16777220 / (ms * 1e-3), "root": rh,
+            "shard_level": pl.level, "subtrees": pl.n_subtrees,
+            "subtrees_per_rank": [e - b for b, e in pl.subtree_ranges]}
+        ms, rh, pl = sharded_ms(2, 32, 1 << 20, True, False, 20)
+        sharded_extras["state_tree_2^20_sharded"] = {
+            "ms": ms, "n_gpus": world, "hashes": (1 << 20) + 20, "root": rh, "shard_level": pl.level,
+            "subtrees_per_rank": [e - b for b, e in pl.subtree_ranges], "depth_field": pl.insert_depth,
+            "root_depth": pl.root_depth}
+        leaves = torch.empty((0, 32), dtype=torch.uint8, device=dev)
+
     # ---- the other BASELINE configs and the "next" rows, rank 0 only, short ---------------------
     extras = {}
     if rank == 0 and not args.no_extras:
@@ -461,7 +498,7 @@ def run_ours(args, rank, world, local_rank):
                        "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / (peak * world),
                        "root": root_hex},
         "bit_exact_sample": ok,
-        "other_configs": extras,
+        "other_configs": dict(extras, **sharded_extras),
     }
     if base:
         line["cpu_baseline"] = base

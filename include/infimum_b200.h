@@ -56,9 +56,11 @@ extern "C" {
 #define INF_ERR_NO_DEVICE 64
 #define INF_ERR_CUDA 65
 #define INF_ERR_OUT_OF_MEMORY 66
+#define INF_ERR_NCCL 67
 
 /* flags */
 #define INF_FLAG_LITTLE_ENDIAN 1u /* hash_bytes_le wire order (poseidon.rs:233-250) */
+#define INF_MULTI_PEER_COPY 1u    /* inf_multi_init: gather subtree roots with peer copies instead of NCCL */
 
 typedef struct inf_ctx inf_ctx;
 
@@ -214,6 +216,26 @@ void inf_tree_destroy(inf_tree* tree);
 int inf_merkle_roots_from_paths(inf_ctx* ctx, uint32_t arity, uint32_t depth, const uint64_t* indices,
                                 const uint8_t* leaves, const uint8_t* paths, uint64_t n,
                                 uint8_t* roots);
+
+/* ---- several GPUs from one process ---------------------------------------------------
+ * For hosts that are a single process (the Rust shim): one context per device,
+ * leaves sharded into contiguous subtrees, ONE ncclAllGather of the subtree
+ * roots (libnccl.so.2 is loaded with dlopen on first use; INF_ERR_NCCL if it is
+ * missing), top levels finished on the first device.  Same results and error
+ * codes as inf_tree_merge.  INF_MULTI_PEER_COPY replaces the collective by
+ * cudaMemcpyPeerAsync (also allows the same device to be listed twice, which
+ * NCCL refuses — used to test the sharding on one GPU). */
+typedef struct inf_multi inf_multi;
+int inf_multi_init(const int* devices, int n_devices, uint32_t flags, inf_multi** out);
+void inf_multi_destroy(inf_multi* m);
+int inf_multi_device_count(const inf_multi* m);
+int inf_multi_tree_merge(inf_multi* m, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
+                         int to_depth, const uint8_t* leaves, uint64_t n_leaves, uint8_t root[32],
+                         uint32_t* insert_depth, uint32_t* root_depth, int* has_root);
+/* n independent hashes, contiguous slices hashed concurrently on all devices. */
+int inf_multi_poseidon_hash_batch(inf_multi* m, uint32_t n_inputs, uint32_t flags,
+                                  const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
+                                  uint8_t* out);
 
 /* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
  * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */

@@ -29,6 +29,8 @@ ERR_BAD_DEPTH = 26
 ERR_NO_DEVICE = 64
 ERR_CUDA = 65
 ERR_OUT_OF_MEMORY = 66
+ERR_NCCL = 67
+MULTI_PEER_COPY = 1
 FLAG_LITTLE_ENDIAN = 1
 
 # every symbol include/infimum_b200.h declares
@@ -38,7 +40,8 @@ EXPORTS = [
     "inf_poseidon_hash_batch_dense", "inf_registration_leaves", "inf_interaction_leaves",
     "inf_registration_leaves_dev", "inf_interaction_leaves_dev", "inf_merkle_zeroes", "inf_empty_ballot_roots",
     "inf_tree_merge", "inf_tree_merge_dev", "inf_tree_reduce_dev", "inf_tree_frontier", "inf_tree_build", "inf_tree_root", "inf_tree_paths",
-    "inf_tree_destroy", "inf_merkle_roots_from_paths", "inf_merge_registrations",
+    "inf_tree_destroy", "inf_merkle_roots_from_paths", "inf_multi_init", "inf_multi_destroy",
+    "inf_multi_device_count", "inf_multi_tree_merge", "inf_multi_poseidon_hash_batch", "inf_merge_registrations",
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
     "inf_measure_imad_peak",
 ]
@@ -114,6 +117,16 @@ def load() -> C.CDLL:
     lib.inf_tree_destroy.restype = None
     lib.inf_merkle_roots_from_paths.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]
     lib.inf_merkle_roots_from_paths.restype = C.c_int
+    lib.inf_multi_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(vp)]
+    lib.inf_multi_init.restype = C.c_int
+    lib.inf_multi_destroy.argtypes = [vp]
+    lib.inf_multi_destroy.restype = None
+    lib.inf_multi_device_count.argtypes = [vp]
+    lib.inf_multi_device_count.restype = C.c_int
+    lib.inf_multi_tree_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint64, vp, u32p, u32p, ip]
+    lib.inf_multi_tree_merge.restype = C.c_int
+    lib.inf_multi_poseidon_hash_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp]
+    lib.inf_multi_poseidon_hash_batch.restype = C.c_int
     lib.inf_merge_registrations.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, u32p]
     lib.inf_merge_registrations.restype = C.c_int
     lib.inf_merge_interactions.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,

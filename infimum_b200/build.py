@@ -28,7 +28,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wno-unknown-pragmas",
                      "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-CU_SOURCES = ["poseidon_t%d.cu" % t for t in range(2, 9)] + ["dense_generic.cu", "leaves.cu", "tree_paths.cu", "imad_peak.cu", "capi.cu"]
+CU_SOURCES = ["poseidon_t%d.cu" % t for t in range(2, 9)] + ["dense_generic.cu", "leaves.cu", "tree_paths.cu", "imad_peak.cu", "multi.cu", "capi.cu"]
 CXX_SOURCES = ["host_params.cpp"]
 HEADERS = ["fr.cuh", "poseidon.cuh", "poseidon_tu.cuh", "launch.h", "host_fr.h", "host_params.h",
            os.path.join(ROOT, "include", "infimum_b200.h")]

@@ -296,6 +296,7 @@ const char* inf_strerror(int code) {
         case INF_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
         case INF_ERR_CUDA: return "CUDA error (see inf_last_cuda_error)";
         case INF_ERR_OUT_OF_MEMORY: return "device out of memory";
+        case INF_ERR_NCCL: return "NCCL unavailable or failed";
         default: return "unknown error code";
     }
 }
@@ -826,6 +827,20 @@ int inf_merge_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8
     if (expected_process) *expected_process = pb ? count / pb + ((count % pb) ? 1u : 0u) : 0u;
     if (expected_tally) *expected_tally = tb ? 1u + registrations_count / tb : 0u;
     return INF_OK;
+}
+
+// ---- internal (multi.cu) -----------------------------------------------------------------
+int inf_internal_stream(inf_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return INF_ERR_NULL_POINTER;
+    *stream = (void*)ctx->stream;
+    return INF_OK;
+}
+int inf_internal_grow_io(inf_ctx* ctx, int which, size_t bytes, void** ptr) {
+    if (!ctx || !ptr || which < 0 || which > 1) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    int rc = grow(ctx, &ctx->io[which], &ctx->io_bytes[which], bytes);
+    *ptr = ctx->io[which];
+    return rc;
 }
 
 int inf_debug_dense_params(uint32_t t, uint32_t* out, size_t out_words) {
