@@ -111,6 +111,71 @@ INF_HD void chain4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint3
 #endif
 }
 
+// Shorter chains (the squaring's triangular rows need 1..3 products).
+INF_HD void chain3(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t& r4,
+                   uint32_t& r5, uint32_t& top, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32  %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32  %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32  %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32  %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32  %5, %9, %10, %5;\n\t"
+        "addc.u32        %6, %6, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#else
+    unsigned __int128 t;
+    t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a1 * b + (((uint64_t)r3 << 32) | r2) + (uint64_t)(t >> 64);
+    r2 = (uint32_t)t; r3 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a2 * b + (((uint64_t)r5 << 32) | r4) + (uint64_t)(t >> 64);
+    r4 = (uint32_t)t; r5 = (uint32_t)(t >> 32);
+    top += (uint32_t)(t >> 64);
+#endif
+}
+INF_HD void chain2(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t& top,
+                   uint32_t a0, uint32_t a1, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32  %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32  %3, %6, %7, %3;\n\t"
+        "addc.u32        %4, %4, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(top)
+        : "r"(a0), "r"(a1), "r"(b));
+#else
+    unsigned __int128 t;
+    t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a1 * b + (((uint64_t)r3 << 32) | r2) + (uint64_t)(t >> 64);
+    r2 = (uint32_t)t; r3 = (uint32_t)(t >> 32);
+    top += (uint32_t)(t >> 64);
+#endif
+}
+INF_HD void chain1(uint32_t& r0, uint32_t& r1, uint32_t& top, uint32_t a0, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32  %1, %3, %4, %1;\n\t"
+        "addc.u32        %2, %2, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(top)
+        : "r"(a0), "r"(b));
+#else
+    unsigned __int128 t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    top += (uint32_t)(t >> 64);
+#endif
+}
+// n products (n = 0..4) into the pairs starting at zc[0], carry into zc[2n].
+INF_HD void chain_n(const int n, uint32_t* zc, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3,
+                    uint32_t b) {
+    if (n == 4) chain4(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], zc[7], zc[8], o0, o1, o2, o3, b);
+    else if (n == 3) chain3(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], o0, o1, o2, b);
+    else if (n == 2) chain2(zc[0], zc[1], zc[2], zc[3], zc[4], o0, o1, b);
+    else if (n == 1) chain1(zc[0], zc[1], zc[2], o0, b);
+}
+
 // Reduction step with the fold of the shared column:
 //   m_col += s_col                      (column i lives in both accumulators)
 //   m      = m_col * (-p^-1) mod 2^32
@@ -283,6 +348,26 @@ struct MontAcc {
                z[A][i + 6], z[A][i + 7], z[A][i + 8], a[0], a[2], a[4], a[6], bi);
     }
 
+    // Row i of a squaring: only the products a_k * a_i with k >= i, the
+    // off-diagonal ones against the doubled operand (36 products instead of
+    // 64).  d = limbs of 2a; e[k] = a[k] << 1 is limb k of 2*(a with limbs
+    // 0..k-1 cleared), which is what multiplies a_i at k = i + 1 (the bit that
+    // d[i+1] inherits from a_i belongs to the diagonal term and must not be
+    // counted twice).  Column i is complete after rows 0..i, as for a product:
+    // every pair (j, k) with j <= k and j + k = i has j <= i.
+    INF_HD void sqr_row(const int i, const uint32_t* a, const uint32_t* d, const uint32_t* e) {
+        const int A = i & 1, S = A ^ 1;
+        const int ke = (i & 1) ? i + 1 : i;      // first even limb index >= i
+        const int ko = (i & 1) ? i : i + 1;      // first odd  limb index >= i
+        const int ne = ke <= 6 ? (8 - ke) / 2 : 0, no = ko <= 7 ? (9 - ko) / 2 : 0;
+#define INF_SQ_OP(k) ((k) > 7 ? 0u : (k) == i ? a[(k)] : ((k) == i + 1 ? e[(k)] : d[(k)]))
+        if (no > 0)
+            chain_n(no, &z[S][i + ko], INF_SQ_OP(ko), INF_SQ_OP(ko + 2), INF_SQ_OP(ko + 4), INF_SQ_OP(ko + 6), a[i]);
+        if (ne > 0)
+            chain_n(ne, &z[A][i + ke], INF_SQ_OP(ke), INF_SQ_OP(ke + 2), INF_SQ_OP(ke + 4), INF_SQ_OP(ke + 6), a[i]);
+#undef INF_SQ_OP
+    }
+
     // Reduction step i (after all terms' row i): fold the column the two
     // accumulators share, then make column i zero by adding m*p*2^(32 i).
     INF_HD void reduce(const int i) {
@@ -319,6 +404,25 @@ INF_HD void mont_mul(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         t.row(i, a, b[i]);
+        t.reduce(i);
+    }
+    t.finish(r);
+}
+
+// r = a*a/R with 36 + 64 wide multiplies instead of 64 + 64.  Needs a < 2^255
+// (true for every value the range discipline lets through) so that 2a fits 8 limbs.
+INF_HD void mont_sqr(uint32_t (&r)[8], const uint32_t* a) {
+    uint32_t d[8], e[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        e[k] = a[k] << 1;
+        d[k] = k == 0 ? e[k] : (e[k] | (a[k - 1] >> 31));
+    }
+    MontAcc t;
+    t.zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        t.sqr_row(i, a, d, e);
         t.reduce(i);
     }
     t.finish(r);

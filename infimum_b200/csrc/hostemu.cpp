@@ -29,6 +29,11 @@ void hostemu_mont_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
     mont_mul(t, a, b);
     memcpy(r, t, 32);
 }
+void hostemu_mont_sqr(const uint32_t* a, uint32_t* r) {
+    uint32_t t[8];
+    mont_sqr(t, a);
+    memcpy(r, t, 32);
+}
 void hostemu_mont_mul_add(const uint32_t* a, const uint32_t* b, const uint32_t* v, uint32_t* r) {
     uint32_t t[8];
     mont_mul_add(t, a, b, v);

@@ -71,8 +71,8 @@ INF_HD void dot(uint32_t (&out)[8], const uint32_t* a, const uint32_t* b, const 
 // x^5
 INF_HD void sbox(uint32_t (&y)[8], const uint32_t (&x)[8]) {
     uint32_t x2[8], x4[8];
-    mont_mul(x2, x, x);
-    mont_mul(x4, x2, x2);
+    mont_sqr(x2, x);
+    mont_sqr(x4, x2);
     mont_mul(y, x4, x);
 }
 

@@ -162,3 +162,20 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
     for j in range(t):
         assert el(k) == mont(T["M"][0][j]); k += 1
     assert k * 8 == words
+
+
+def test_mont_sqr_equals_mul(emu):
+    rng = random.Random(77)
+    lim = 2 * P + (1 << 224)
+    cases = [x % lim for x in EDGE_VALUES] + [rng.randrange(lim) for _ in range(3000)]
+    cases += [(1 << 255) - 1, 0x7FFFFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF,
+              int("80000000" * 7 + "00000001", 16) >> 1, int("ffffffff" * 7, 16), int("80000000" * 8, 16) >> 1]
+    base = emu.hostemu_overflow_count()
+    for a in cases:
+        assert a < (1 << 255)
+        r, q = U8(), U8()
+        emu.hostemu_mont_sqr(limbs(a), r)
+        emu.hostemu_mont_mul(limbs(a), limbs(a), q)
+        assert val(r) == val(q), hex(a)
+        assert val(r) % P == a * a * RINV % P
+    assert emu.hostemu_overflow_count() == base
