@@ -407,6 +407,25 @@ def run_ours(args, rank, world, local_rank):
         extras["message_tree_2^26"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
                                        "root_depth": rdp, "roofline_frac": nh * W_HASH5 / (ms * 1e-3) / 1e12 / (sms_peak),
                                        "root": root_hex5}
+        # end to end for the tree: 2^24 leaves in pinned host memory -> root (inf_tree_merge uploads in
+        # chunks that overlap with level-0 hashing)
+        h_leaves = torch.empty((1 << 24, 32), dtype=torch.uint8).pin_memory()
+        h_leaves.copy_(lv[: 1 << 24])
+        hl = h_leaves.numpy()
+        root = C.create_string_buffer(32)
+        idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            rc = ctx.lib.inf_tree_merge(ctx.handle, 2, 24, 0, 1, hl.ctypes.data, 1 << 24, root, C.byref(idp),
+                                        C.byref(rdp), C.byref(has))
+            dt = time.perf_counter() - t0
+            assert rc in (0, 2), rc
+            best = dt if best is None else min(best, dt)
+        extras["tree_merge_2^24_e2e"] = {"ms": best * 1e3, "h2d_bytes": (1 << 24) * 32, "d2h_bytes": 32,
+                                         "api": "inf_tree_merge (pinned host leaves -> root)", "root": root.raw.hex()}
+        del h_leaves, hl
         # hash5 batch (t = 6), 2^22 tuples
         n5 = 1 << 22
         d5 = lv[: 5 * n5]

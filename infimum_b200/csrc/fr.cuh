@@ -412,6 +412,9 @@ INF_HD void mont_mul(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b) {
 // r = a*a/R with 36 + 64 wide multiplies instead of 64 + 64.  Needs a < 2^255
 // (true for every value the range discipline lets through) so that 2a fits 8 limbs.
 INF_HD void mont_sqr(uint32_t (&r)[8], const uint32_t* a) {
+#if defined(INF_HOST_CHECKS) && !defined(__CUDA_ARCH__)
+    if (a[7] >> 31) host_overflow_count++;          // precondition a < 2^255
+#endif
     uint32_t d[8], e[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
