@@ -31,8 +31,16 @@ __device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
     p[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// Two resident blocks (255 registers): the fused kernel spills 504 bytes at the
+// 168-register cap and is 17 % slower there (measured, tools/leaf_probe.py:
+// 20.8 vs 24.4 M messages/s); at 2 blocks it runs at the sum of its parts
+// (2 x hash5 + hash4 = 41 ns per message).
+#ifndef INF_LEAF_MIN_BLOCKS
+#define INF_LEAF_MIN_BLOCKS 2
+#endif
+
 // pk: n x (x, y) 32-byte big-endian; data: n x 10 x 32 bytes; out: n x 32 bytes
-__global__ void __launch_bounds__(INF_BLOCK, 3)
+__global__ void __launch_bounds__(INF_BLOCK, INF_LEAF_MIN_BLOCKS)
 interaction_leaf_kernel(const uint4* __restrict__ pk, const uint4* __restrict__ data,
                         uint4* __restrict__ out, uint64_t n) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
