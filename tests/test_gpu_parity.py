@@ -435,3 +435,31 @@ def test_retained_tree_paths(ib, arity, depth, blank, n):
     roots = ib.merkle_roots_from_paths(arity, depth, idx, np.stack([np.frombuffer(logical[int(i)], dtype=np.uint8) for i in idx]), paths)
     assert all(roots[k].tobytes() == tree.root for k in range(len(idx)))
     tree.close()
+
+
+# ---- extremes --------------------------------------------------------------------------------------
+def test_maximum_depths_and_empty_inputs(ib):
+    """Deepest trees the pallet admits (lib.rs:390-399: 2^depth and 5^depth must
+    fit u32 -> registration depth <= 31, interaction depth <= 13) plus the 33-level
+    zero table's limit, with a handful of leaves: all padding levels are walked."""
+    lv = random_fr_bytes(3, seed=404)
+    for arity, full_depth, blank in ((2, 31, True), (2, 32, False), (5, 13, False), (5, 32, False)):
+        rc, root, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, True, lv)
+        t = ib.PollStateTree.new(arity, full_depth, (0, ib.get_merkle_zeroes(arity)[0]) if blank else None)
+        t.extend(lv).merge(True)
+        assert rc == 0 and t.root == root and t.depth == depth
+    with pytest.raises(ValueError):
+        ib.PollStateTree.new(2, 33).extend(lv).merge(True)          # beyond the zero table
+    # empty batch, empty tree
+    h = ib.Poseidon.new_circom(2)
+    assert h.hash_batch(b"").shape == (0, 32)
+    t = ib.new_interaction_tree(3)
+    t.merge(True)
+    assert t.root is None and t.count == 0 and t.hashes == []       # merge on an empty frontier (state.rs:240-248)
+    o = O.new_interaction_tree(3)
+    o.merge(True)
+    assert o.root is None
+    # merge_registrations on an empty registration tree: the blank leaf alone is the root
+    t, c = ib.merge_registrations(ib.new_registration_tree(10))
+    o, oc = O.merge_registrations(O.new_registration_tree(10))
+    assert t.root == o.root and c == oc
