@@ -98,7 +98,11 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     }
 
     // ---- partial rounds -----------------------------------------------------
-#pragma unroll 1
+#ifndef INF_PARTIAL_UNROLL
+#define INF_PARTIAL_UNROLL 1
+#endif
+    constexpr int kPartialUnroll = INF_PARTIAL_UNROLL;   // > 1 only for instruction-cache experiments
+#pragma unroll kPartialUnroll
     for (int j = 0; j < L::RP; j++) {
         const uint32_t* pt = tbl + (L::PART + j * L::PART_STRIDE) * 8;
         sbox(x[0], s[0]);

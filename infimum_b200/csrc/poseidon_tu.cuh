@@ -9,6 +9,8 @@
 //   tree_level_kernel   one tree level, arity T-1, zero padded  K2
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "launch.h"
 #include "poseidon.cuh"
 
@@ -119,6 +121,28 @@ path_root_kernel(const uint64_t* __restrict__ indices, const uint4* __restrict__
 #define INF_CAT2(a, b) a##b
 #define INF_CAT(a, b) INF_CAT2(a, b)
 
+// Resident blocks per SM.  The multiply pipe saturates at 12 warps per SM; more
+// resident warps only add instruction-cache misses (the partial-round body is
+// 21-35 KB and every warp sits at a different place in it): measured for t=3,
+// 5 blocks/SM 135.3, 4 blocks 136.3, 3 blocks 138.8, 2 blocks 135.4 M hash2/s
+// (profiles/r01_occupancy_sweep.md).  Widths >= 4 are held at 3 blocks by their
+// register count; widths 2 and 3 (94 registers) are held there by reserving
+// dynamic shared memory they do not use.  INF_SMEM_PAD overrides (experiments).
+static int occupancy_pad() {
+    static int pad = -1;
+    if (pad < 0) {
+        const char* e = getenv("INF_SMEM_PAD");
+        pad = e ? atoi(e) : (T <= 3 ? 74 * 1024 : 0);
+        if (pad > 48 * 1024) {
+            cudaFuncSetAttribute(hash_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            cudaFuncSetAttribute(hash_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+            cudaFuncSetAttribute(path_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        }
+    }
+    return pad;
+}
+
 cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t words) {
     if (words != (size_t)Layout<T>::WORDS) return cudaErrorInvalidValue;
     return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
@@ -128,10 +152,11 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
                                                 const TagArg& tag, bool le, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    const int pad = occupancy_pad();
     if (le)
-        hash_batch_kernel<true><<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        hash_batch_kernel<true><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
     else
-        hash_batch_kernel<false><<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        hash_batch_kernel<false><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
     return cudaGetLastError();
 }
 
@@ -142,7 +167,7 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift
     Node32 z;
     memcpy(z.w, zero_be, 32);
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
-    tree_level_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
+    tree_level_kernel<<<grid, INF_BLOCK, occupancy_pad(), st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
     return cudaGetLastError();
 }
 
@@ -151,7 +176,7 @@ cudaError_t INF_CAT(launch_path_root_t, INF_T)(const void* d_idx, const void* d_
                                                uint64_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
-    path_root_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint64_t*)d_idx, (const uint4*)d_leaves,
+    path_root_kernel<<<grid, INF_BLOCK, occupancy_pad(), st>>>((const uint64_t*)d_idx, (const uint4*)d_leaves,
                                                  (const uint4*)d_paths, depth, (uint4*)d_roots, n);
     return cudaGetLastError();
 }
