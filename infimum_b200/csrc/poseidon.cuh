@@ -29,6 +29,18 @@ INF_HD constexpr int partial_rounds(int t) {
          : t == 8 ? 64 : t == 9 ? 63 : t == 10 ? 60 : t == 11 ? 66 : t == 12 ? 60 : 65;
 }
 
+// Paired partial rounds (widths >= 4 with an even number of partial rounds):
+// two partial rounds share the update of s[1..]:
+//     round A:  x_a = s0^5 ;  n  = row0_A . (x_a, s[1..]) + k_A
+//     round B:  x_b = n^5  ;  s0 = row0_B . (x_b, s[1..]) + c_B * x_a + k_B ,   c_B = row0_B[1..] . w_A
+//     then      s_i += w_A[i] * x_a + w_B[i] * x_b          (one 2-term lazy dot, ONE reduction)
+// which is the same arithmetic (s_i after round A is s_i + w_A[i] x_a, substituted
+// into round B's row) with T-1 fewer reductions and one more product per pair:
+// -7 % (t=4) .. -10 % (t=6) multiply-pipe instructions per round.  t = 3 does
+// not use it: its loop body would double to 42 KB and the instruction fetch
+// costs more than the 4.6 % saved (profiles/r01_occupancy_sweep.md).
+INF_HD constexpr bool paired_rounds(int t) { return t >= 4 && partial_rounds(t) % 2 == 0; }
+
 // Table layout, in units of one field element (8 x u32).  All entries are
 // Montgomery form (x*R mod p) except the "V" entries, which are x*R^2 mod p
 // (they enter an accumulator that is then divided by R), and OUT_ROW, which is
@@ -43,9 +55,13 @@ struct Layout {
     static constexpr int PRE_M = FULL_M + T * T;         // [T][T] MDS with the sparse prefix merged
     static constexpr int FULL_V = PRE_M + T * T;         // [3][T] C_{r+1}, r = 0..2
     static constexpr int PRE_V = FULL_V + 3 * T;         // [T]   (k_0, 0, ..., 0)
-    static constexpr int PART = PRE_V + T;               // [RP][2T]: row0[T], w[T-1], kv
-    static constexpr int PART_STRIDE = 2 * T;
-    static constexpr int LAST_D = PART + RP * PART_STRIDE;   // [T-1]  D[1..] * R (added once)
+    static constexpr bool PAIRED = paired_rounds(T);
+    // unpaired: [RP][2T]      : row0[T], w[T-1], kv
+    // paired:   [RP/2][4T+1]  : row0_A[T], kv_A, row0_B[T], c_B, kv_B, (w_A[i], w_B[i]) for i = 1..T-1
+    static constexpr int PART = PRE_V + T;
+    static constexpr int PART_STRIDE = PAIRED ? 4 * T + 1 : 2 * T;
+    static constexpr int PART_COUNT = PAIRED ? RP / 2 : RP;
+    static constexpr int LAST_D = PART + PART_COUNT * PART_STRIDE;   // [T-1]  D[1..] * R (added once)
     static constexpr int TAIL_V = LAST_D + (T - 1);      // [3][T] C_{4+RP+r+1}, r = 0..2
     static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
     static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
@@ -98,6 +114,39 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     }
 
     // ---- partial rounds -----------------------------------------------------
+    if constexpr (L::PAIRED) {
+        // q[0] = S-box output of the current round, q[1..T-1] = s[1..T-1],
+        // q[T] = x_a, q[T+1] = x_b (contiguous so that the lazy dots can stride over them)
+        uint32_t q[T + 2][8];
+#pragma unroll
+        for (int i = 1; i < T; i++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[i][k] = s[i][k];
+#pragma unroll 1
+        for (int j = 0; j < L::PART_COUNT; j++) {
+            const uint32_t* pt = tbl + (L::PART + j * L::PART_STRIDE) * 8;
+            uint32_t n[8];
+            sbox(q[0], s[0]);                                                   // round A
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[T][k] = q[0][k];
+            dot<T, 8>(n, &q[0][0], pt, pt + T * 8);
+            sbox(q[0], n);                                                      // round B
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[T + 1][k] = q[0][k];
+            dot<T + 1, 8>(s[0], &q[0][0], pt + (T + 1) * 8, pt + (2 * T + 2) * 8);
+#pragma unroll
+            for (int i = 1; i < T; i++) {                                       // s_i += w_A x_a + w_B x_b
+                uint32_t w[8];
+                dot<2, 8>(w, &q[T][0], pt + (2 * T + 3 + 2 * (i - 1)) * 8, nullptr);
+                add8(q[i], q[i], w);
+                csub2p(q[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 1; i < T; i++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[i][k] = q[i][k];
+    } else {
 #ifndef INF_PARTIAL_UNROLL
 #define INF_PARTIAL_UNROLL 1
 #endif
@@ -121,6 +170,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) s[0][k] = n0[k];
+    }
     }
     // remaining constants of the first tail round on elements 1..T-1
 #pragma unroll

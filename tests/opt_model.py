@@ -109,3 +109,39 @@ def hash_opt(inputs, tag=0, tables=None):
         if r + 1 < 8 + rp:
             s = [(a + b) % P for a, b in zip(s, C[r + 1])]
     return s[0]
+
+
+def paired(t):
+    """Widths whose kernels pair partial rounds (poseidon.cuh paired_rounds)."""
+    return t >= 4 and poseidon_parameters(t)[3] % 2 == 0
+
+
+def hash_opt_paired(inputs, tag=0, tables=None):
+    """Same schedule with the partial rounds taken two at a time, the way the
+    kernels for widths >= 4 run them: s[1..] is updated once per pair and round
+    B's row sees round A's update through the scalar c_B = row0_B[1..] . w_A."""
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    rp, M, C = T["rp"], T["M"], T["C"]
+    assert rp % 2 == 0
+    sb = lambda x: pow(x, 5, P)
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    s = _matvec(T["PRE"], [sb(x) for x in s])
+    s[0] = (s[0] + T["k"][0]) % P
+    kv = lambda j: T["k"][j + 1] if j + 1 < rp else T["D"][0]
+    for jp in range(rp // 2):
+        (rowA, wA), (rowB, wB) = T["sparse"][2 * jp], T["sparse"][2 * jp + 1]
+        xa = sb(s[0])
+        n = (rowA[0] * xa + sum(a * b for a, b in zip(rowA[1:], s[1:])) + kv(2 * jp)) % P
+        xb = sb(n)
+        cB = sum(a * b for a, b in zip(rowB[1:], wA)) % P
+        s0 = (rowB[0] * xb + sum(a * b for a, b in zip(rowB[1:], s[1:])) + cB * xa + kv(2 * jp + 1)) % P
+        s = [s0] + [(s[i] + wA[i - 1] * xa + wB[i - 1] * xb) % P for i in range(1, t)]
+    s = [s[0]] + [(a + b) % P for a, b in zip(s[1:], T["D"][1:])]
+    for r in range(4 + rp, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(a + b) % P for a, b in zip(s, C[r + 1])]
+    return s[0]

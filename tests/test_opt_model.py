@@ -17,3 +17,12 @@ def test_optimised_schedule_equals_dense(t):
     for ins in cases:
         for tag in (0, 5):
             assert opt_model.hash_opt(ins, tag, tables) == O.poseidon_permute_hash(ins, tag)
+
+
+@pytest.mark.parametrize("t", [t for t in range(2, 14) if opt_model.paired(t)])
+def test_paired_partial_rounds_equal_dense(t):
+    rng = random.Random(2000 + t)
+    tables = opt_model.derive(t)
+    for ins in ([1] * (t - 1), [O.P - 1] * (t - 1), [rng.randrange(O.P) for _ in range(t - 1)]):
+        for tag in (0, 9):
+            assert opt_model.hash_opt_paired(ins, tag, tables) == O.poseidon_permute_hash(ins, tag)
