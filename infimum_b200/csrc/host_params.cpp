@@ -205,28 +205,25 @@ std::vector<uint32_t> build_opt(void) {
         for (int i = 0; i < T; i++) put_v(tbl, L::FULL_V + r * T + i, C(r + 1, i));
     put_v(tbl, L::PRE_V + 0, k[0]);     // remaining PRE_V entries stay zero
     auto kv = [&](int j) -> const F& { return j + 1 < rp ? k[j + 1] : D[0]; };   // constant folded into round j's row
-    if (L::PAIRED) {
-        for (int jp = 0; jp < rp / 2; jp++) {
-            const int a = 2 * jp, b = 2 * jp + 1, base = L::PART + jp * L::PART_STRIDE;
-            for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[a][i]);
-            put_v(tbl, base + T, kv(a));
-            for (int i = 0; i < T; i++) put_mont(tbl, base + T + 1 + i, row0[b][i]);
-            F c = zero();                                          // c_B = row0_B[1..] . w_A
-            for (int i = 0; i < T - 1; i++) c = add(c, mul(row0[b][i + 1], wcol[a][i]));
-            put_mont(tbl, base + 2 * T + 1, c);
-            put_v(tbl, base + 2 * T + 2, kv(b));
-            for (int i = 0; i < T - 1; i++) {
-                put_mont(tbl, base + 2 * T + 3 + 2 * i, wcol[a][i]);
-                put_mont(tbl, base + 2 * T + 4 + 2 * i, wcol[b][i]);
-            }
+    for (int jp = 0; jp < L::N_PAIRS; jp++) {
+        const int a = 2 * jp, b = 2 * jp + 1, base = L::PART + jp * L::PAIR_STRIDE;
+        for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[a][i]);
+        put_v(tbl, base + T, kv(a));
+        for (int i = 0; i < T; i++) put_mont(tbl, base + T + 1 + i, row0[b][i]);
+        F c = zero();                                          // c_B = row0_B[1..] . w_A
+        for (int i = 0; i < T - 1; i++) c = add(c, mul(row0[b][i + 1], wcol[a][i]));
+        put_mont(tbl, base + 2 * T + 1, c);
+        put_v(tbl, base + 2 * T + 2, kv(b));
+        for (int i = 0; i < T - 1; i++) {
+            put_mont(tbl, base + 2 * T + 3 + 2 * i, wcol[a][i]);
+            put_mont(tbl, base + 2 * T + 4 + 2 * i, wcol[b][i]);
         }
-    } else {
-        for (int j = 0; j < rp; j++) {
-            const int base = L::PART + j * L::PART_STRIDE;
-            for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[j][i]);
-            for (int i = 0; i < T - 1; i++) put_mont(tbl, base + T + i, wcol[j][i]);
-            put_v(tbl, base + 2 * T - 1, kv(j));
-        }
+    }
+    for (int js = 0; js < L::N_SINGLES; js++) {
+        const int j = 2 * L::N_PAIRS + js, base = L::SINGLES + js * L::SINGLE_STRIDE;
+        for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[j][i]);
+        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + T + i, wcol[j][i]);
+        put_v(tbl, base + 2 * T - 1, kv(j));
     }
     for (int i = 1; i < T; i++) put_mont(tbl, L::LAST_D + i - 1, D[i]);
     for (int r = 0; r < 3; r++)

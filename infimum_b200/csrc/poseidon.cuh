@@ -36,10 +36,16 @@ INF_HD constexpr int partial_rounds(int t) {
 //     then      s_i += w_A[i] * x_a + w_B[i] * x_b          (one 2-term lazy dot, ONE reduction)
 // which is the same arithmetic (s_i after round A is s_i + w_A[i] x_a, substituted
 // into round B's row) with T-1 fewer reductions and one more product per pair:
-// -7 % (t=4) .. -10 % (t=6) multiply-pipe instructions per round.  t = 3 does
-// not use it: its loop body would double to 42 KB and the instruction fetch
-// costs more than the 4.6 % saved (profiles/r01_occupancy_sweep.md).
-INF_HD constexpr bool paired_rounds(int t) { return t >= 4 && partial_rounds(t) % 2 == 0; }
+// -4.6 % (t=3) .. -10 % (t=6) multiply-pipe instructions per round.  An odd number
+// of partial rounds (t = 3, 7) leaves one ordinary round at the end.  (The pair
+// doubles the loop body; at 5 resident blocks per SM that cost t=3 more in
+// instruction fetch than it saved, at the shipped 3 blocks it costs nothing —
+// profiles/r01_occupancy_sweep.md.)  INF_NO_PAIRING builds the unpaired form.
+#ifdef INF_NO_PAIRING
+INF_HD constexpr bool paired_rounds(int) { return false; }
+#else
+INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
+#endif
 
 // Table layout, in units of one field element (8 x u32).  All entries are
 // Montgomery form (x*R mod p) except the "V" entries, which are x*R^2 mod p
@@ -56,12 +62,16 @@ struct Layout {
     static constexpr int FULL_V = PRE_M + T * T;         // [3][T] C_{r+1}, r = 0..2
     static constexpr int PRE_V = FULL_V + 3 * T;         // [T]   (k_0, 0, ..., 0)
     static constexpr bool PAIRED = paired_rounds(T);
-    // unpaired: [RP][2T]      : row0[T], w[T-1], kv
-    // paired:   [RP/2][4T+1]  : row0_A[T], kv_A, row0_B[T], c_B, kv_B, (w_A[i], w_B[i]) for i = 1..T-1
+    // single round record [2T]   : row0[T], w[T-1], kv
+    // pair record        [4T+1] : row0_A[T], kv_A, row0_B[T], c_B, kv_B, (w_A[i], w_B[i]) for i = 1..T-1
+    // PAIRED: RP/2 pair records, then one single record if RP is odd; else RP single records.
     static constexpr int PART = PRE_V + T;
-    static constexpr int PART_STRIDE = PAIRED ? 4 * T + 1 : 2 * T;
-    static constexpr int PART_COUNT = PAIRED ? RP / 2 : RP;
-    static constexpr int LAST_D = PART + PART_COUNT * PART_STRIDE;   // [T-1]  D[1..] * R (added once)
+    static constexpr int PAIR_STRIDE = 4 * T + 1;
+    static constexpr int SINGLE_STRIDE = 2 * T;
+    static constexpr int N_PAIRS = PAIRED ? RP / 2 : 0;
+    static constexpr int N_SINGLES = PAIRED ? RP % 2 : RP;
+    static constexpr int SINGLES = PART + N_PAIRS * PAIR_STRIDE;
+    static constexpr int LAST_D = SINGLES + N_SINGLES * SINGLE_STRIDE;   // [T-1]  D[1..] * R (added once)
     static constexpr int TAIL_V = LAST_D + (T - 1);      // [3][T] C_{4+RP+r+1}, r = 0..2
     static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
     static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
@@ -69,8 +79,8 @@ struct Layout {
     static constexpr int WORDS = COUNT * 8;
 };
 
-// out = ( sum_j a[j] * tbl[b_off + j] + tbl[v_off] ) / R, then the cheap range step.
-template <int N, int STRIDE_A>
+// out = ( sum_j a[j] * b[j] + V ) / R, then (RANGE_STEP) the cheap range step.
+template <int N, int STRIDE_A, bool RANGE_STEP = true>
 INF_HD void dot(uint32_t (&out)[8], const uint32_t* a, const uint32_t* b, const uint32_t* v) {
     MontAcc acc;
     if (v) acc.init(v); else acc.zero();
@@ -81,7 +91,7 @@ INF_HD void dot(uint32_t (&out)[8], const uint32_t* a, const uint32_t* b, const 
         acc.reduce(i);
     }
     acc.finish(out);
-    csub2p(out);
+    if (RANGE_STEP) csub2p(out);
 }
 
 // x^5
@@ -114,7 +124,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     }
 
     // ---- partial rounds -----------------------------------------------------
-    if constexpr (L::PAIRED) {
+    if constexpr (L::N_PAIRS > 0) {
         // q[0] = S-box output of the current round, q[1..T-1] = s[1..T-1],
         // q[T] = x_a, q[T+1] = x_b (contiguous so that the lazy dots can stride over them)
         uint32_t q[T + 2][8];
@@ -123,8 +133,8 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
 #pragma unroll
             for (int k = 0; k < 8; k++) q[i][k] = s[i][k];
 #pragma unroll 1
-        for (int j = 0; j < L::PART_COUNT; j++) {
-            const uint32_t* pt = tbl + (L::PART + j * L::PART_STRIDE) * 8;
+        for (int j = 0; j < L::N_PAIRS; j++) {
+            const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
             uint32_t n[8];
             sbox(q[0], s[0]);                                                   // round A
 #pragma unroll
@@ -137,7 +147,8 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
 #pragma unroll
             for (int i = 1; i < T; i++) {                                       // s_i += w_A x_a + w_B x_b
                 uint32_t w[8];
-                dot<2, 8>(w, &q[T][0], pt + (2 * T + 3 + 2 * (i - 1)) * 8, nullptr);
+                // (x_a, x_b < 1.6 p, constants < p: w < 1.61 p, no range step needed before the add)
+                dot<2, 8, false>(w, &q[T][0], pt + (2 * T + 3 + 2 * (i - 1)) * 8, nullptr);
                 add8(q[i], q[i], w);
                 csub2p(q[i]);
             }
@@ -146,14 +157,10 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         for (int i = 1; i < T; i++)
 #pragma unroll
             for (int k = 0; k < 8; k++) s[i][k] = q[i][k];
-    } else {
-#ifndef INF_PARTIAL_UNROLL
-#define INF_PARTIAL_UNROLL 1
-#endif
-    constexpr int kPartialUnroll = INF_PARTIAL_UNROLL;   // > 1 only for instruction-cache experiments
-#pragma unroll kPartialUnroll
-    for (int j = 0; j < L::RP; j++) {
-        const uint32_t* pt = tbl + (L::PART + j * L::PART_STRIDE) * 8;
+    }
+#pragma unroll 1
+    for (int j = 0; j < L::N_SINGLES; j++) {
+        const uint32_t* pt = tbl + (L::SINGLES + j * L::SINGLE_STRIDE) * 8;
         sbox(x[0], s[0]);
         // element 0 temporarily holds the S-box output so that the dot runs
         // over the contiguous state
@@ -170,7 +177,6 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) s[0][k] = n0[k];
-    }
     }
     // remaining constants of the first tail round on elements 1..T-1
 #pragma unroll

@@ -112,8 +112,9 @@ def hash_opt(inputs, tag=0, tables=None):
 
 
 def paired(t):
-    """Widths whose kernels pair partial rounds (poseidon.cuh paired_rounds)."""
-    return t >= 4 and poseidon_parameters(t)[3] % 2 == 0
+    """Widths whose kernels pair partial rounds (poseidon.cuh paired_rounds): all
+    of 2..8; an odd round count leaves one ordinary round at the end."""
+    return t >= 2
 
 
 def hash_opt_paired(inputs, tag=0, tables=None):
@@ -123,7 +124,6 @@ def hash_opt_paired(inputs, tag=0, tables=None):
     t = len(inputs) + 1
     T = tables or derive(t)
     rp, M, C = T["rp"], T["M"], T["C"]
-    assert rp % 2 == 0
     sb = lambda x: pow(x, 5, P)
     s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
     for r in range(3):
@@ -139,6 +139,11 @@ def hash_opt_paired(inputs, tag=0, tables=None):
         cB = sum(a * b for a, b in zip(rowB[1:], wA)) % P
         s0 = (rowB[0] * xb + sum(a * b for a, b in zip(rowB[1:], s[1:])) + cB * xa + kv(2 * jp + 1)) % P
         s = [s0] + [(s[i] + wA[i - 1] * xa + wB[i - 1] * xb) % P for i in range(1, t)]
+    if rp % 2:                                      # the odd round out, in the ordinary form
+        row0, w = T["sparse"][rp - 1]
+        x0 = sb(s[0])
+        new0 = (row0[0] * x0 + sum(a * b for a, b in zip(row0[1:], s[1:])) + kv(rp - 1)) % P
+        s = [new0] + [(s[i] + w[i - 1] * x0) % P for i in range(1, t)]
     s = [s[0]] + [(a + b) % P for a, b in zip(s[1:], T["D"][1:])]
     for r in range(4 + rp, 8 + rp):
         s = _matvec(M, [sb(x) for x in s])

@@ -146,27 +146,26 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
     for i in range(1, t):
         assert el(k) == 0; k += 1
     kvf = lambda j: vform(T["k"][j + 1] if j + 1 < rp else T["D"][0])
-    if opt_model.paired(t):
-        for jp in range(rp // 2):
-            (rowA, wA), (rowB, wB) = T["sparse"][2 * jp], T["sparse"][2 * jp + 1]
-            for i in range(t):
-                assert el(k) == mont(rowA[i]); k += 1
-            assert el(k) == kvf(2 * jp); k += 1
-            for i in range(t):
-                assert el(k) == mont(rowB[i]); k += 1
-            assert el(k) == mont(sum(a * b for a, b in zip(rowB[1:], wA)) % P); k += 1
-            assert el(k) == kvf(2 * jp + 1); k += 1
-            for i in range(t - 1):
-                assert el(k) == mont(wA[i]); k += 1
-                assert el(k) == mont(wB[i]); k += 1
-    else:
-        for j in range(rp):
-            row0, w = T["sparse"][j]
-            for i in range(t):
-                assert el(k) == mont(row0[i]); k += 1
-            for i in range(t - 1):
-                assert el(k) == mont(w[i]); k += 1
-            assert el(k) == kvf(j); k += 1
+    n_pairs = rp // 2 if opt_model.paired(t) else 0
+    for jp in range(n_pairs):
+        (rowA, wA), (rowB, wB) = T["sparse"][2 * jp], T["sparse"][2 * jp + 1]
+        for i in range(t):
+            assert el(k) == mont(rowA[i]); k += 1
+        assert el(k) == kvf(2 * jp); k += 1
+        for i in range(t):
+            assert el(k) == mont(rowB[i]); k += 1
+        assert el(k) == mont(sum(a * b for a, b in zip(rowB[1:], wA)) % P); k += 1
+        assert el(k) == kvf(2 * jp + 1); k += 1
+        for i in range(t - 1):
+            assert el(k) == mont(wA[i]); k += 1
+            assert el(k) == mont(wB[i]); k += 1
+    for j in range(2 * n_pairs, rp):
+        row0, w = T["sparse"][j]
+        for i in range(t):
+            assert el(k) == mont(row0[i]); k += 1
+        for i in range(t - 1):
+            assert el(k) == mont(w[i]); k += 1
+        assert el(k) == kvf(j); k += 1
     for i in range(1, t):
         assert el(k) == mont(T["D"][i]); k += 1
     for r in range(3):

@@ -22,7 +22,9 @@ def csub2p(x):
 
 
 def sbox(x, track):
+    assert x < 2 ** 255 / P, x                               # mont_sqr needs 2a to fit 8 limbs
     x2 = dot([(x, x)], 0); track(x2)
+    assert x2 < 2 ** 255 / P
     x4 = dot([(x2, x2)], 0); track(x4)
     x5 = dot([(x4, x)], 0); track(x5)
     return x5
@@ -40,7 +42,13 @@ def run(t, rp):
     for r in range(4):                                       # first half
         x = [sbox(v, track) for v in s]
         s = [csub2p(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
-    for j in range(rp):                                      # partial rounds
+    for j in range(rp // 2):                                 # paired partial rounds
+        xa = sbox(s[0], track)
+        n = csub2p(track(dot([(xa, 1.0)] + [(si, 1.0) for si in s[1:]])))
+        xb = sbox(n, track)
+        n0 = csub2p(track(dot([(xb, 1.0)] + [(si, 1.0) for si in s[1:]] + [(xa, 1.0)])))
+        s = [n0] + [csub2p(track(si + track(dot([(xa, 1.0), (xb, 1.0)], 0)))) for si in s[1:]]
+    for j in range(rp % 2):                                  # the odd round out
         x0 = sbox(s[0], track)
         n0 = csub2p(track(dot([(x0, 1.0)] + [(si, 1.0) for si in s[1:]])))
         s = [n0] + [csub2p(track(si + track(dot([(x0, 1.0)], 0)))) for si in s[1:]]
