@@ -488,8 +488,9 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": "theoretical: %d SMs x 64 IMAD/clk x %.0f MHz (BASELINE.md 2)" % (sms, sm_max_mhz),
         "peak_measured": meas, "frac_of_measured_imad": achieved / meas["imad"] if meas.get("imad") else None,
         "avg_launch_ms": avg_launch_ms,
-        "note": "frac is reference-equivalent work: the kernel runs the sparse/lazy schedule (594 field mults, "
-                "~68k IMAD-pipe instructions per hash2), so frac may exceed 1; executed pipe utilisation is in profiles/",
+        "note": "frac is reference-equivalent work: the kernel runs the sparse/lazy/paired schedule (594 field "
+                "mults, 162 of them squarings, ~62.5k IMAD-pipe instructions per hash2), so frac may exceed 1; "
+                "executed multiply-pipe utilisation (96 % busy) is in profiles/r01_hash2_ncu_summary.md",
         "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "bytes_per_hash": 96},
     }
