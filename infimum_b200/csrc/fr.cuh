@@ -167,13 +167,112 @@ INF_HD void chain1(uint32_t& r0, uint32_t& r1, uint32_t& top, uint32_t a0, uint3
     top += (uint32_t)(t >> 64);
 #endif
 }
+// The same chains without the final carry (callers prove it is zero).
+INF_HD void chain4_nt(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t& r4,
+                   uint32_t& r5, uint32_t& r6, uint32_t& r7, uint32_t a0,
+                   uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
+        "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
+        "madc.lo.cc.u32  %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32  %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
+        "madc.hi.cc.u32  %7, %11, %12, %7;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+    unsigned __int128 t;
+    t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a1 * b + (((uint64_t)r3 << 32) | r2) + (uint64_t)(t >> 64);
+    r2 = (uint32_t)t; r3 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a2 * b + (((uint64_t)r5 << 32) | r4) + (uint64_t)(t >> 64);
+    r4 = (uint32_t)t; r5 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a3 * b + (((uint64_t)r7 << 32) | r6) + (uint64_t)(t >> 64);
+    r6 = (uint32_t)t; r7 = (uint32_t)(t >> 32);
+#if defined(INF_HOST_CHECKS)
+    if ((uint32_t)(t >> 64)) host_overflow_count++;     // proven zero: see MontAcc::row
+#endif
+#endif
+}
+
+INF_HD void chain3_nt(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t& r4,
+                   uint32_t& r5, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %6, %9, %0;\n\t"
+        "madc.hi.cc.u32  %1, %6, %9, %1;\n\t"
+        "madc.lo.cc.u32  %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32  %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32  %4, %8, %9, %4;\n\t"
+        "madc.hi.cc.u32  %5, %8, %9, %5;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#else
+    unsigned __int128 t;
+    t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a1 * b + (((uint64_t)r3 << 32) | r2) + (uint64_t)(t >> 64);
+    r2 = (uint32_t)t; r3 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a2 * b + (((uint64_t)r5 << 32) | r4) + (uint64_t)(t >> 64);
+    r4 = (uint32_t)t; r5 = (uint32_t)(t >> 32);
+#if defined(INF_HOST_CHECKS)
+    if ((uint32_t)(t >> 64)) host_overflow_count++;     // proven zero: see MontAcc::row
+#endif
+#endif
+}
+
+INF_HD void chain2_nt(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                   uint32_t a0, uint32_t a1, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32  %1, %4, %6, %1;\n\t"
+        "madc.lo.cc.u32  %2, %5, %6, %2;\n\t"
+        "madc.hi.cc.u32  %3, %5, %6, %3;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)
+        : "r"(a0), "r"(a1), "r"(b));
+#else
+    unsigned __int128 t;
+    t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+    t = (unsigned __int128)a1 * b + (((uint64_t)r3 << 32) | r2) + (uint64_t)(t >> 64);
+    r2 = (uint32_t)t; r3 = (uint32_t)(t >> 32);
+#if defined(INF_HOST_CHECKS)
+    if ((uint32_t)(t >> 64)) host_overflow_count++;     // proven zero: see MontAcc::row
+#endif
+#endif
+}
+
+INF_HD void chain1_nt(uint32_t& r0, uint32_t& r1, uint32_t a0, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32   %0, %2, %3, %0;\n\t"
+        "madc.hi.cc.u32  %1, %2, %3, %1;"
+        : "+r"(r0), "+r"(r1)
+        : "r"(a0), "r"(b));
+#else
+    unsigned __int128 t = (unsigned __int128)a0 * b + (((uint64_t)r1 << 32) | r0);
+    r0 = (uint32_t)t; r1 = (uint32_t)(t >> 32);
+#if defined(INF_HOST_CHECKS)
+    if ((uint32_t)(t >> 64)) host_overflow_count++;     // proven zero: see MontAcc::row
+#endif
+#endif
+}
+
 // n products (n = 0..4) into the pairs starting at zc[0], carry into zc[2n].
 INF_HD void chain_n(const int n, uint32_t* zc, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3,
-                    uint32_t b) {
-    if (n == 4) chain4(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], zc[7], zc[8], o0, o1, o2, o3, b);
-    else if (n == 3) chain3(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], o0, o1, o2, b);
-    else if (n == 2) chain2(zc[0], zc[1], zc[2], zc[3], zc[4], o0, o1, b);
-    else if (n == 1) chain1(zc[0], zc[1], zc[2], o0, b);
+                    uint32_t b, const bool top = true) {
+    if (top) {
+        if (n == 4) chain4(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], zc[7], zc[8], o0, o1, o2, o3, b);
+        else if (n == 3) chain3(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], o0, o1, o2, b);
+        else if (n == 2) chain2(zc[0], zc[1], zc[2], zc[3], zc[4], o0, o1, b);
+        else if (n == 1) chain1(zc[0], zc[1], zc[2], o0, b);
+    } else {
+        if (n == 4) chain4_nt(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], zc[6], zc[7], o0, o1, o2, o3, b);
+        else if (n == 3) chain3_nt(zc[0], zc[1], zc[2], zc[3], zc[4], zc[5], o0, o1, o2, b);
+        else if (n == 2) chain2_nt(zc[0], zc[1], zc[2], zc[3], o0, o1, b);
+        else if (n == 1) chain1_nt(zc[0], zc[1], o0, b);
+    }
 }
 
 // Reduction step with the fold of the shared column:
@@ -339,9 +438,17 @@ struct MontAcc {
         for (int c = 0; c < 8; c++) z[0][c] = v[c];
     }
 
-    // Row i of one term: accumulate a * bi * 2^(32 i).
-    INF_HD void row(const int i, const uint32_t* a, const uint32_t bi) {
+    // Row i of one term: accumulate a * bi * 2^(32 i).  `first`: this is the first
+    // term of row i.  Then the odd-limb chain is the first thing to touch the pair
+    // (i+7, i+8) of its accumulator in this pass — column i+8 is still zero and
+    // column i+7 holds only a few carries — so its carry out is provably zero
+    // ((2^32-1)^2 + small < 2^64) and the final addc is dropped.
+    INF_HD void row(const int i, const uint32_t* a, const uint32_t bi, const bool first = false) {
         const int A = i & 1, S = A ^ 1;   // aligned / shifted accumulator for this row
+        if (first)
+            chain4_nt(z[S][i + 1], z[S][i + 2], z[S][i + 3], z[S][i + 4], z[S][i + 5], z[S][i + 6],
+                      z[S][i + 7], z[S][i + 8], a[1], a[3], a[5], a[7], bi);
+        else
         chain4(z[S][i + 1], z[S][i + 2], z[S][i + 3], z[S][i + 4], z[S][i + 5], z[S][i + 6],
                z[S][i + 7], z[S][i + 8], z[S][i + 9], a[1], a[3], a[5], a[7], bi);
         chain4(z[A][i], z[A][i + 1], z[A][i + 2], z[A][i + 3], z[A][i + 4], z[A][i + 5],
@@ -361,8 +468,9 @@ struct MontAcc {
         const int ko = (i & 1) ? i : i + 1;      // first odd  limb index >= i
         const int ne = ke <= 6 ? (8 - ke) / 2 : 0, no = ko <= 7 ? (9 - ko) / 2 : 0;
 #define INF_SQ_OP(k) ((k) > 7 ? 0u : (k) == i ? a[(k)] : ((k) == i + 1 ? e[(k)] : d[(k)]))
-        if (no > 0)
-            chain_n(no, &z[S][i + ko], INF_SQ_OP(ko), INF_SQ_OP(ko + 2), INF_SQ_OP(ko + 4), INF_SQ_OP(ko + 6), a[i]);
+        if (no > 0)   // first (only) chain on the pair (i+7, i+8): no carry out, as in row()
+            chain_n(no, &z[S][i + ko], INF_SQ_OP(ko), INF_SQ_OP(ko + 2), INF_SQ_OP(ko + 4), INF_SQ_OP(ko + 6), a[i],
+                    false);
         if (ne > 0)
             chain_n(ne, &z[A][i + ke], INF_SQ_OP(ke), INF_SQ_OP(ke + 2), INF_SQ_OP(ke + 4), INF_SQ_OP(ke + 6), a[i]);
 #undef INF_SQ_OP
@@ -403,7 +511,7 @@ INF_HD void mont_mul(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b) {
     t.zero();
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        t.row(i, a, b[i]);
+        t.row(i, a, b[i], true);
         t.reduce(i);
     }
     t.finish(r);
@@ -438,7 +546,7 @@ INF_HD void mont_mul_add(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b,
     t.init(v);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        t.row(i, a, b[i]);
+        t.row(i, a, b[i], true);
         t.reduce(i);
     }
     t.finish(r);

@@ -32,6 +32,7 @@ def sbox(x, track):
 
 def run(t, rp):
     worst = [0.0]
+    rs = csub2p if t > 2 else (lambda x: x)                  # poseidon.cuh: RS = T > 2
 
     def track(x):
         worst[0] = max(worst[0], x)
@@ -41,21 +42,21 @@ def run(t, rp):
     s = [track(dot([(LIM, 1.0)]))] * t                     # absorb: raw 256-bit x R^2 + V
     for r in range(4):                                       # first half
         x = [sbox(v, track) for v in s]
-        s = [csub2p(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
+        s = [rs(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
     for j in range(rp // 2):                                 # paired partial rounds
         xa = sbox(s[0], track)
-        n = csub2p(track(dot([(xa, 1.0)] + [(si, 1.0) for si in s[1:]])))
+        n = rs(track(dot([(xa, 1.0)] + [(si, 1.0) for si in s[1:]])))
         xb = sbox(n, track)
-        n0 = csub2p(track(dot([(xb, 1.0)] + [(si, 1.0) for si in s[1:]] + [(xa, 1.0)])))
+        n0 = rs(track(dot([(xb, 1.0)] + [(si, 1.0) for si in s[1:]] + [(xa, 1.0)])))
         s = [n0] + [csub2p(track(si + track(dot([(xa, 1.0), (xb, 1.0)], 0)))) for si in s[1:]]
     for j in range(rp % 2):                                  # the odd round out
         x0 = sbox(s[0], track)
-        n0 = csub2p(track(dot([(x0, 1.0)] + [(si, 1.0) for si in s[1:]])))
+        n0 = rs(track(dot([(x0, 1.0)] + [(si, 1.0) for si in s[1:]])))
         s = [n0] + [csub2p(track(si + track(dot([(x0, 1.0)], 0)))) for si in s[1:]]
     s = [s[0]] + [csub2p(track(si + 1.0)) for si in s[1:]]
     for r in range(3):
         x = [sbox(v, track) for v in s]
-        s = [csub2p(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
+        s = [rs(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
     x = [sbox(v, track) for v in s]
     out = track(dot([(xi, 1.0) for xi in x], 0))
     out = csub2p(out)
