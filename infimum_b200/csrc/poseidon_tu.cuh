@@ -79,6 +79,180 @@ tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
     store_node(out + 2 * idx, ow);
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative tree level, for the levels near the root.
+//
+// A level with fewer nodes than resident threads costs one single-thread hash
+// latency (~190 us: a lone warp needs 810 cycles per dependent multiplication,
+// profiles/r01_imad_microbench.md) whatever its size.  Here T warps share 32
+// hashes: warp w owns state element w of all 32 (lane = hash), the warps run on
+// different sub-partitions, and the state is staged through shared memory:
+//   full round     every warp: own S-box, publish it, barrier, own MDS row
+//                  (1 S-box + 1 row instead of T + T on the critical path)
+//   partial pair   warp 0 carries the chain S-box, row A, S-box, row B; warps
+//                  1..T-1 take their  s_w += w_A x_a + w_B x_b  off it
+// Same tables, same arithmetic, so results are bit-identical to the per-thread
+// kernel; the critical path drops ~1.5x (t=3) / ~2x (t=6).
+// Shared layout [element][limb][lane]: consecutive lanes hit consecutive banks.
+struct CoopSmem {
+    uint32_t x[2][T][8][32];      // S-box outputs of a full round, double buffered
+    uint32_t s[T][8][32];         // s[1..T-1] as of the start of the current pair
+    uint32_t xa[8][32], xb[8][32];
+};
+
+__device__ __forceinline__ void sm_put(uint32_t (*dst)[32], const uint32_t (&v)[8], int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) dst[k][lane] = v[k];
+}
+__device__ __forceinline__ void sm_get(uint32_t* v, const uint32_t (*src)[32], int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = src[k][lane];
+}
+
+__global__ void __launch_bounds__(32 * T, 1)
+tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
+                       uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
+    using L = Layout<T>;
+    constexpr int A = T - 1;
+    extern __shared__ __align__(16) unsigned char coop_raw[];
+    CoopSmem& sm = *reinterpret_cast<CoopSmem*>(coop_raw);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t h = (uint64_t)blockIdx.x * 32 + lane;
+    const bool live = h < n_out;          // dead lanes run along on zeros (barriers are block wide)
+    const uint32_t* tbl = c_tbl;
+
+    // ---- absorb: warp w >= 1 takes child w-1 of its hash ---------------------
+    uint32_t s[8];
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = tbl[L::S0 * 8 + k];
+    } else {
+        uint32_t wd[8], raw[8];
+        const uint64_t j = h * A + (w - 1);
+        if (live && j >= shift && j - shift < n_in) {
+            load_node(wd, in + 2 * (j - shift));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) wd[k] = zero.w[k];
+        }
+        words_to_limbs<false>(raw, wd);
+        absorb<T>(s, raw, w, tbl);
+    }
+
+    uint32_t xs[T + 1][8];
+    // ---- first half: rounds 0..3 -----------------------------------------------
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::PRE_M) * 8;
+        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::PRE_V) * 8;
+        uint32_t x[8];
+        sbox(x, s);
+        sm_put(sm.x[r & 1][w], x, lane);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[r & 1][i], lane);
+        dot<T, 8>(s, &xs[0][0], m + w * T * 8, v + w * 8);
+    }
+
+    // ---- partial rounds ------------------------------------------------------------
+    if (w > 0) sm_put(sm.s[w], s, lane);
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
+    }
+#pragma unroll 1
+    for (int j = 0; j < L::N_PAIRS; j++) {
+        const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
+        if (w == 0) {
+            uint32_t n[8];
+            sbox(xs[0], s);                                   // round A
+            sm_put(sm.xa, xs[0], lane);
+#pragma unroll
+            for (int k = 0; k < 8; k++) xs[T][k] = xs[0][k];
+            __syncthreads();                                  // (A) x_a published
+            dot<T, 8>(n, &xs[0][0], pt, pt + T * 8);
+            sbox(xs[0], n);                                   // round B
+            sm_put(sm.xb, xs[0], lane);
+            __syncthreads();                                  // (B) x_b published
+            dot<T + 1, 8>(s, &xs[0][0], pt + (T + 1) * 8, pt + (2 * T + 2) * 8);
+            __syncthreads();                                  // (C) s[1..] updated by the others
+#pragma unroll
+            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
+        } else {
+            uint32_t ab[2][8], d[8];
+            __syncthreads();                                  // (A)
+            sm_get(ab[0], sm.xa, lane);
+            __syncthreads();                                  // (B)
+            sm_get(ab[1], sm.xb, lane);
+            dot<2, 8, false>(d, &ab[0][0], pt + (2 * T + 3 + 2 * (w - 1)) * 8, nullptr);
+            add8(s, s, d);
+            csub2p(s);
+            sm_put(sm.s[w], s, lane);
+            __syncthreads();                                  // (C)
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < L::N_SINGLES; j++) {                  // the odd round out
+        const uint32_t* pt = tbl + (L::SINGLES + j * L::SINGLE_STRIDE) * 8;
+        if (w == 0) {
+            uint32_t n[8];
+            sbox(xs[0], s);
+            sm_put(sm.xa, xs[0], lane);
+            __syncthreads();                                  // (A)
+            dot<T, 8>(n, &xs[0][0], pt, pt + (2 * T - 1) * 8);
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = n[k];
+            __syncthreads();                                  // (C)
+#pragma unroll
+            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
+        } else {
+            uint32_t xa[8], d[8];
+            __syncthreads();                                  // (A)
+            sm_get(xa, sm.xa, lane);
+            mont_mul(d, xa, pt + (T + w - 1) * 8);
+            add8(s, s, d);
+            csub2p(s);
+            sm_put(sm.s[w], s, lane);
+            __syncthreads();                                  // (C)
+        }
+    }
+    if (w > 0) {                                              // remaining constants of the first tail round
+        add8(s, s, tbl + (L::LAST_D + w - 1) * 8);
+        csub2p(s);
+    }
+
+    // ---- second half: 3 full rounds, then the output row -------------------------
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+        const uint32_t* m = tbl + L::FULL_M * 8;
+        const uint32_t* v = tbl + (L::TAIL_V + r * T) * 8;
+        uint32_t x[8];
+        sbox(x, s);
+        sm_put(sm.x[r & 1][w], x, lane);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[r & 1][i], lane);
+        dot<T, 8>(s, &xs[0][0], m + w * T * 8, v + w * 8);
+    }
+    {
+        uint32_t x[8];
+        sbox(x, s);
+        sm_put(sm.x[1][w], x, lane);                          // rounds 0..2 left buffer 0 last
+        __syncthreads();
+    }
+    if (w == 0 && live) {
+#pragma unroll
+        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[1][i], lane);
+        uint32_t hsh[8], ow[8];
+        dot<T, 8>(hsh, &xs[0][0], tbl + L::OUT_ROW * 8, nullptr);
+        csub_p_exact(hsh);
+        csub_p_exact(hsh);
+        limbs_to_words<false>(ow, hsh);
+        store_node(out + 2 * h, ow);
+    }
+}
+
 // Batched compute_merkle_root_from_path (pallet/src/poll/provider.rs:396-436):
 // one path per thread.  At every level the node sits at position idx % A among
 // its A-1 siblings (which are stored in order, skipping that position), the A
@@ -160,12 +334,31 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
     return cudaGetLastError();
 }
 
+// Levels with at most this many parents go to the warp-cooperative kernel (they
+// are latency-bound either way; INF_COOP_MAX overrides, 0 disables).
+static uint64_t coop_max() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("INF_COOP_MAX");
+        v = e ? atoll(e) : 8192;
+        cudaFuncSetAttribute(tree_level_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CoopSmem));
+    }
+    return (uint64_t)v;
+}
+
 cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift, uint64_t n_in,
                                                 void* d_out, uint64_t n_out,
                                                 const uint8_t* zero_be, cudaStream_t st) {
     if (n_out == 0) return cudaSuccess;
     Node32 z;
     memcpy(z.w, zero_be, 32);
+    if (n_out <= coop_max()) {
+        const unsigned grid = (unsigned)((n_out + 31) / 32);
+        tree_level_coop_kernel<<<grid, 32 * T, sizeof(CoopSmem), st>>>((const uint4*)d_in, shift, n_in,
+                                                                       (uint4*)d_out, n_out, z);
+        return cudaGetLastError();
+    }
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
     tree_level_kernel<<<grid, INF_BLOCK, occupancy_pad(), st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
     return cudaGetLastError();
