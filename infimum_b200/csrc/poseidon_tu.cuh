@@ -89,15 +89,23 @@ tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
 // different sub-partitions, and the state is staged through shared memory:
 //   full round     every warp: own S-box, publish it, barrier, own MDS row
 //                  (1 S-box + 1 row instead of T + T on the critical path)
-//   partial pair   warp 0 carries the chain S-box, row A, S-box, row B; warps
-//                  1..T-1 take their  s_w += w_A x_a + w_B x_b  off it
-// Same tables, same arithmetic, so results are bit-identical to the per-thread
-// kernel; the critical path drops ~1.5x (t=3) / ~2x (t=6).
+//   partial pair   warp 0 carries only the chain  S-box, x_a*m00, S-box, x_b*m00':
+//                  the products of the two rows that do not involve the fresh
+//                  S-box output (s_w*rowA[w], s_w*rowB[w], c_B*x_a) and the updates
+//                  s_w += w_A x_a + w_B x_b are formed by warps 1..T-1 meanwhile
+//                  and only added in (separately reduced, so the sums agree mod p)
+// Same tables, same field values, so results are bit-identical to the per-thread
+// kernel; per pair the critical path is 944 multiply-pipe instructions instead
+// of 1 664 (t=3) / 2 648 (t=6).
 // Shared layout [element][limb][lane]: consecutive lanes hit consecutive banks.
 struct CoopSmem {
     uint32_t x[2][T][8][32];      // S-box outputs of a full round, double buffered
-    uint32_t s[T][8][32];         // s[1..T-1] as of the start of the current pair
-    uint32_t xa[8][32], xb[8][32];
+    // partial rounds, everything double buffered by pair parity:
+    uint32_t xa[2][8][32], xb[2][8][32];   // S-box outputs of rounds A and B (warp 0)
+    uint32_t pa[2][T][8][32];              // s_w * rowA[w] / R   (warp w >= 1)
+    uint32_t pb[2][T][8][32];              // s_w * rowB[w] / R   (warp w >= 1)
+    uint32_t cx[2][8][32];                 // c_B * x_a / R       (warp 1)
+    uint32_t s[T][8][32];                  // s[1..T-1] for the odd round out
 };
 
 __device__ __forceinline__ void sm_put(uint32_t (*dst)[32], const uint32_t (&v)[8], int lane) {
@@ -155,66 +163,83 @@ tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_
     }
 
     // ---- partial rounds ------------------------------------------------------------
-    if (w > 0) sm_put(sm.s[w], s, lane);
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
-    }
+    // Pair j, buffers of parity j & 1.  Two barriers per pair:
+    //   before (A): warp 0 publishes x_a; warp w >= 1 publishes s_w*rowA[w] and s_w*rowB[w]
+    //   before (B): warp 0 forms n = x_a*m00 + k_A + sum pa, publishes x_b = n^5;
+    //               warp 1 publishes c_B*x_a
+    //   after  (B): warp 0 forms s_0 = x_b*m00' + k_B + sum pb + cx;
+    //               warp w >= 1 updates s_w += w_A x_a + w_B x_b  and runs ahead into pair j+1
+    // A buffer of parity p is rewritten in pair j+2 only by warps that have passed
+    // barrier (B) of pair j+1, which its readers of pair j reach after reading it.
 #pragma unroll 1
     for (int j = 0; j < L::N_PAIRS; j++) {
         const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
+        const int p = j & 1;
         if (w == 0) {
-            uint32_t n[8];
-            sbox(xs[0], s);                                   // round A
-            sm_put(sm.xa, xs[0], lane);
+            uint32_t xa[8], xb[8], n[8], t[8];
+            sbox(xa, s);                                              // round A
+            sm_put(sm.xa[p], xa, lane);
+            __syncthreads();                                          // (A)
+            mont_mul_add(n, xa, pt, pt + T * 8);                      // x_a*m00 + k_A
 #pragma unroll
-            for (int k = 0; k < 8; k++) xs[T][k] = xs[0][k];
-            __syncthreads();                                  // (A) x_a published
-            dot<T, 8>(n, &xs[0][0], pt, pt + T * 8);
-            sbox(xs[0], n);                                   // round B
-            sm_put(sm.xb, xs[0], lane);
-            __syncthreads();                                  // (B) x_b published
-            dot<T + 1, 8>(s, &xs[0][0], pt + (T + 1) * 8, pt + (2 * T + 2) * 8);
-            __syncthreads();                                  // (C) s[1..] updated by the others
+            for (int i = 1; i < T; i++) {
+                sm_get(t, sm.pa[p][i], lane);
+                add8(n, n, t);
+                csub2p(n);
+            }
+            sbox(xb, n);                                              // round B
+            sm_put(sm.xb[p], xb, lane);
+            __syncthreads();                                          // (B)
+            mont_mul_add(s, xb, pt + (T + 1) * 8, pt + (2 * T + 2) * 8);   // x_b*m00' + k_B
 #pragma unroll
-            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
-        } else {
-            uint32_t ab[2][8], d[8];
-            __syncthreads();                                  // (A)
-            sm_get(ab[0], sm.xa, lane);
-            __syncthreads();                                  // (B)
-            sm_get(ab[1], sm.xb, lane);
-            dot<2, 8, false>(d, &ab[0][0], pt + (2 * T + 3 + 2 * (w - 1)) * 8, nullptr);
-            add8(s, s, d);
+            for (int i = 1; i < T; i++) {
+                sm_get(t, sm.pb[p][i], lane);
+                add8(s, s, t);
+                csub2p(s);
+            }
+            sm_get(t, sm.cx[p], lane);
+            add8(s, s, t);
             csub2p(s);
-            sm_put(sm.s[w], s, lane);
-            __syncthreads();                                  // (C)
+        } else {
+            uint32_t t[8], ab[2][8];
+            mont_mul(t, s, pt + w * 8);                               // s_w * rowA[w]
+            sm_put(sm.pa[p][w], t, lane);
+            mont_mul(t, s, pt + (T + 1 + w) * 8);                     // s_w * rowB[w]
+            sm_put(sm.pb[p][w], t, lane);
+            __syncthreads();                                          // (A)
+            sm_get(ab[0], sm.xa[p], lane);
+            if (w == 1) {
+                mont_mul(t, ab[0], pt + (2 * T + 1) * 8);             // c_B * x_a
+                sm_put(sm.cx[p], t, lane);
+            }
+            __syncthreads();                                          // (B)
+            sm_get(ab[1], sm.xb[p], lane);
+            dot<2, 8, false>(t, &ab[0][0], pt + (2 * T + 3 + 2 * (w - 1)) * 8, nullptr);
+            add8(s, s, t);
+            csub2p(s);
         }
     }
-#pragma unroll 1
-    for (int j = 0; j < L::N_SINGLES; j++) {                  // the odd round out
-        const uint32_t* pt = tbl + (L::SINGLES + j * L::SINGLE_STRIDE) * 8;
+    if (L::N_SINGLES > 0) {                                           // the odd round out, in the plain form
+        if (w > 0) sm_put(sm.s[w], s, lane);
+        __syncthreads();
+        const uint32_t* pt = tbl + L::SINGLES * 8;
         if (w == 0) {
             uint32_t n[8];
+#pragma unroll
+            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
             sbox(xs[0], s);
-            sm_put(sm.xa, xs[0], lane);
-            __syncthreads();                                  // (A)
+            sm_put(sm.xa[0], xs[0], lane);
+            __syncthreads();
             dot<T, 8>(n, &xs[0][0], pt, pt + (2 * T - 1) * 8);
 #pragma unroll
             for (int k = 0; k < 8; k++) s[k] = n[k];
-            __syncthreads();                                  // (C)
-#pragma unroll
-            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
         } else {
             uint32_t xa[8], d[8];
-            __syncthreads();                                  // (A)
-            sm_get(xa, sm.xa, lane);
+            __syncthreads();
+            sm_get(xa, sm.xa[0], lane);
             mont_mul(d, xa, pt + (T + w - 1) * 8);
             add8(s, s, d);
             csub2p(s);
-            sm_put(sm.s[w], s, lane);
-            __syncthreads();                                  // (C)
         }
     }
     if (w > 0) {                                              // remaining constants of the first tail round
@@ -335,12 +360,13 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
 }
 
 // Levels with at most this many parents go to the warp-cooperative kernel (they
-// are latency-bound either way; INF_COOP_MAX overrides, 0 disables).
+// are latency-bound either way; measured best 16 384..32 768 on B200, tools/tree_probe.py;
+// INF_COOP_MAX overrides, 0 disables).
 static uint64_t coop_max() {
     static long long v = -1;
     if (v < 0) {
         const char* e = getenv("INF_COOP_MAX");
-        v = e ? atoll(e) : 8192;
+        v = e ? atoll(e) : 16384;
         cudaFuncSetAttribute(tree_level_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CoopSmem));
     }
