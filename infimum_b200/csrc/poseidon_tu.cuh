@@ -329,15 +329,19 @@ path_root_kernel(const uint64_t* __restrict__ indices, const uint4* __restrict__
 // dynamic shared memory they do not use.  INF_SMEM_PAD overrides (experiments).
 static int occupancy_pad() {
     static int pad = -1;
+    static bool set_on[64] = {};          // the opt-in above 48 KB is a per-device function attribute
     if (pad < 0) {
         const char* e = getenv("INF_SMEM_PAD");
         pad = e ? atoi(e) : (T <= 3 ? 74 * 1024 : 0);
-        if (pad > 48 * 1024) {
-            cudaFuncSetAttribute(hash_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-            cudaFuncSetAttribute(hash_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-            cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-            cudaFuncSetAttribute(path_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        }
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pad > 48 * 1024 && dev >= 0 && dev < 64 && !set_on[dev]) {
+        cudaFuncSetAttribute(hash_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        cudaFuncSetAttribute(hash_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        cudaFuncSetAttribute(path_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        set_on[dev] = true;
     }
     return pad;
 }
@@ -364,11 +368,17 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
 // INF_COOP_MAX overrides, 0 disables).
 static uint64_t coop_max() {
     static long long v = -1;
+    static bool set_on[64] = {};
     if (v < 0) {
         const char* e = getenv("INF_COOP_MAX");
         v = e ? atoll(e) : 16384;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sizeof(CoopSmem) > 48 * 1024 && dev >= 0 && dev < 64 && !set_on[dev]) {
         cudaFuncSetAttribute(tree_level_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CoopSmem));
+        set_on[dev] = true;
     }
     return (uint64_t)v;
 }
