@@ -30,6 +30,47 @@ def test_emulated_world_on_one_gpu(world):
         assert plan.insert_depth == depth
 
 
+
+def test_maximum_size_2_28_leaves():
+    """SURVEY.md 8(d) config 5's largest size (8 GiB of leaves, 64-bit indexing on
+    every level).  (1) Binary tree over [x]*2^28, merged to full depth, equals 28
+    chained self-hashes from the oracle.  (2) Quinary tree (depth 13) over 2^28
+    distinct leaves: the root of the whole equals the root over its 8-rank
+    shards' roots."""
+    import ctypes as C
+    import infimum_b200 as ib
+    from infimum_b200 import sharded
+    ctx = ib.get_context(0)
+    n = 1 << 28
+    x = random_fr_bytes(1, seed=28)
+    lv = torch.from_numpy(x).cuda().repeat(n, 1)
+    root = C.create_string_buffer(32)
+    a, b, h = C.c_uint32(), C.c_uint32(), C.c_int()
+
+    def merge(arity, depth):
+        rc = ctx.lib.inf_tree_merge_dev(ctx.handle, arity, depth, 0, 1, lv.data_ptr(), n, root, C.byref(a), C.byref(b),
+                                        C.byref(h), None)
+        assert rc in (0, 2), rc
+        return root.raw
+
+    node = x[0].tobytes()
+    for _ in range(28):
+        node = c_oracle.hash_one([node, node])
+    assert merge(2, 28) == node and b.value == 28
+    # distinct leaves: a counter in the low 8 bytes of every leaf
+    idx = torch.arange(n, dtype=torch.int64, device="cuda")
+    for k in range(8):
+        lv[:, 31 - k] = ((idx >> (8 * k)) & 0xFF).to(torch.uint8)
+    del idx
+    whole = merge(5, 13)
+    plan = sharded.make_plan(5, 13, n, False, True, 8)
+    assert plan.n_subtrees >= 32
+    got = sharded.emulated_sharded_merge(lv, plan, sharded.GpuBackend(ctx, 0))
+    assert got.cpu().numpy().tobytes() == whole
+    del lv
+    torch.cuda.empty_cache()
+
+
 WORKER = r"""
 import os, sys, json
 import torch, torch.distributed as dist
