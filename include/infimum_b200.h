@@ -259,7 +259,11 @@ int inf_debug_dense_params(uint32_t t, uint32_t* out, size_t out_words);
 int inf_debug_opt_table(uint32_t t, uint32_t* out, size_t out_words);
 /* Sustained 32-bit IMAD issue rate of the device, measured with independent
  * multiply-add chains on every SM sub-partition.  kind 0: IMAD (lo), kind 1:
- * IMAD.WIDE.U32 counted as 2 IMAD-equivalents each.  Result in IMAD/s. */
+ * IMAD.WIDE.U32 counted as 2 IMAD-equivalents each, kind 2: the carry-linked
+ * chains the field product uses (same unit), kind 3: IMAD.HI.  Result in
+ * IMAD/s.  kinds 4-6 probe the FP64 pipe for a double-precision formulation
+ * of the product: DFMA alone, DFMA + IMAD.WIDE 1:1 and 2:1; result in
+ * instructions/s. */
 int inf_measure_imad_peak(inf_ctx* ctx, int kind, double* imad_per_s, double* sm_clock_mhz);
 
 #ifdef __cplusplus

@@ -55,6 +55,12 @@ namespace {
 int cuda_fail(inf_ctx* ctx, cudaError_t e, const char* what) {
     if (ctx) {
         ctx->last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+        // Do not return to the caller with copies into or out of its buffers still
+        // in flight on the context's streams (the chunked host paths queue several).
+        for (int i = 0; i < 3; i++)
+            if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
     }
     return e == cudaErrorMemoryAllocation ? INF_ERR_OUT_OF_MEMORY : INF_ERR_CUDA;
 }
@@ -319,6 +325,7 @@ int inf_init(int device, inf_ctx** out) {
         inf_destroy(ctx);
         return rc;
     };
+    if (!bind.ok) return fail(INF_ERR_NO_DEVICE);
     cudaError_t e;
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
         return fail(cuda_fail(nullptr, e, "cudaDeviceGetAttribute"));
@@ -399,6 +406,7 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
     int rc = check_hash_args(ctx, n_inputs, d_in, n, d_out);
     if (rc) return rc;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     return hash_batch_dev(ctx, n_inputs, flags, domain_tag, d_in, n, d_out,
                           stream ? (cudaStream_t)stream : ctx->stream, false);
 }
@@ -413,6 +421,7 @@ static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, cons
     if (rc) return rc;
     if (n == 0) return INF_OK;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     const uint64_t super = 1ull << 24;                 // device staging is sized for at most 2^24 hashes
     const uint64_t chunk = 1ull << 19;
     const size_t in_row = (size_t)n_inputs * 32;
@@ -476,6 +485,7 @@ int inf_registration_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint
     if (n && (!public_keys || !timestamps || !leaves)) return INF_ERR_NULL_POINTER;
     if (n == 0) return INF_OK;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     return rows_pipeline(ctx, public_keys, 64, (const uint8_t*)timestamps, 8, n, leaves,
                          [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
                              return launch_registration_leaves(a, b, o, c, st);
@@ -488,6 +498,7 @@ int inf_interaction_leaves(inf_ctx* ctx, const uint8_t* public_keys, const uint8
     if (n && (!public_keys || !data || !leaves)) return INF_ERR_NULL_POINTER;
     if (n == 0) return INF_OK;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     return rows_pipeline(ctx, public_keys, 64, data, 320, n, leaves,
                          [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
                              return launch_interaction_leaves(a, b, o, c, st);
@@ -499,6 +510,7 @@ int inf_registration_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const v
     if (!ctx) return INF_ERR_NULL_POINTER;
     if (n && (!d_public_keys || !d_timestamps || !d_leaves)) return INF_ERR_NULL_POINTER;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(launch_registration_leaves(d_public_keys, d_timestamps, d_leaves, n,
                                   stream ? (cudaStream_t)stream : ctx->stream));
     return INF_OK;
@@ -509,6 +521,7 @@ int inf_interaction_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const vo
     if (!ctx) return INF_ERR_NULL_POINTER;
     if (n && (!d_public_keys || !d_data || !d_leaves)) return INF_ERR_NULL_POINTER;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(launch_interaction_leaves(d_public_keys, d_data, d_leaves, n, stream ? (cudaStream_t)stream : ctx->stream));
     return INF_OK;
 }
@@ -530,6 +543,7 @@ int inf_tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pr
                        uint32_t* insert_depth, uint32_t* root_depth, int* has_root, void* stream) {
     if (!ctx) return INF_ERR_NULL_POINTER;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, d_leaves, n_leaves,
                           root, insert_depth, root_depth, has_root,
                           stream ? (cudaStream_t)stream : ctx->stream);
@@ -543,6 +557,7 @@ int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepen
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (full_depth > 32) return INF_ERR_BAD_DEPTH;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     // capacity check before moving any data (insert would have failed first)
     if (n_leaves + (prepend_blank_leaf ? 1 : 0) > pow_sat(arity, full_depth)) {
         if (insert_depth) *insert_depth = 0;
@@ -566,6 +581,7 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (level_in + n_levels > 32) return INF_ERR_BAD_DEPTH;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
     const uint64_t n_total = n_in + shift;
@@ -616,6 +632,7 @@ int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pre
     if (n_total > capacity) return INF_ERR_TREE_ALREADY_FULL;
     if (n_total == 0) return INF_OK;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
     cudaStream_t st = ctx->stream;
     int rc;
@@ -685,6 +702,7 @@ int inf_tree_build(inf_ctx* ctx, uint32_t arity, uint32_t depth, int prepend_bla
     if (n_total > pow_sat(arity, depth)) return INF_ERR_TREE_ALREADY_FULL;
     if (n_total == 0) return INF_ERR_MERGE_FAILED;             // nothing to build a tree over
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     inf_tree* t = new inf_tree();
     t->ctx = ctx; t->arity = arity; t->depth = depth; t->shift = shift; t->n_leaves = n_leaves;
     uint64_t total_nodes = 0, c = n_total;
@@ -723,6 +741,7 @@ int inf_tree_root(inf_tree* tree, uint8_t root[32]) {
     if (!tree || !root) return INF_ERR_NULL_POINTER;
     inf_ctx* ctx = tree->ctx;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(cudaMemcpy(root, (char*)tree->d_nodes + tree->offsets[tree->depth] * 32, 32, cudaMemcpyDeviceToHost));
     return INF_OK;
 }
@@ -733,6 +752,7 @@ int inf_tree_paths(inf_tree* tree, const uint64_t* leaf_indices, uint64_t n_idx,
     if (n_idx == 0 || tree->depth == 0) return INF_OK;
     inf_ctx* ctx = tree->ctx;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     const uint64_t cap = pow_sat(tree->arity, tree->depth);
     for (uint64_t i = 0; i < n_idx; i++)
         if (leaf_indices[i] >= cap) return INF_ERR_BAD_DEPTH;
@@ -770,6 +790,7 @@ int inf_merkle_roots_from_paths(inf_ctx* ctx, uint32_t arity, uint32_t depth, co
     if (n && (!indices || !leaves || !roots || (depth && !paths))) return INF_ERR_NULL_POINTER;
     if (n == 0) return INF_OK;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     const size_t path_bytes = (size_t)n * depth * (arity - 1) * 32;
     const size_t idx_bytes = (n * 8 + 31) & ~(size_t)31;          // keep the nodes 32-byte aligned
     int rc;
@@ -838,6 +859,7 @@ int inf_internal_stream(inf_ctx* ctx, void** stream) {
 int inf_internal_grow_io(inf_ctx* ctx, int which, size_t bytes, void** ptr) {
     if (!ctx || !ptr || which < 0 || which > 1) return INF_ERR_NULL_POINTER;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     int rc = grow(ctx, &ctx->io[which], &ctx->io_bytes[which], bytes);
     *ptr = ctx->io[which];
     return rc;
@@ -865,6 +887,7 @@ int inf_debug_opt_table(uint32_t t, uint32_t* out, size_t out_words) {
 int inf_measure_imad_peak(inf_ctx* ctx, int kind, double* imad_per_s, double* sm_clock_mhz) {
     if (!ctx || !imad_per_s) return INF_ERR_NULL_POINTER;
     Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
     double clk = 0;
     CU(launch_imad_peak(kind, ctx->sm_count, imad_per_s, &clk, ctx->stream));
     if (sm_clock_mhz) *sm_clock_mhz = clk;

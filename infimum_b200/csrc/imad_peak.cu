@@ -130,6 +130,41 @@ __global__ void __launch_bounds__(256) imad_hi_kernel(uint32_t* sink, uint32_t a
     if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+// kind 4: fma.rn.f64 alone (DFMA), 8 independent chains -- the FP64 pipe's rate, for
+// judging a 52-bit-limb double-precision formulation of the field product.
+// kind 5: DFMA and IMAD.WIDE.U32 interleaved 1:1 (16 + 16 per iteration), kind 6: 2:1
+// (the ratio a hi/lo split product needs): do the two pipes overlap?
+template <int DF, int WIDE>
+__global__ void __launch_bounds__(256) dfma_mix_kernel(uint32_t* sink, uint32_t a, uint32_t b,
+                                                        long long* cycles) {
+    double d[CHAINS];
+    unsigned long long x[CHAINS];
+    const double fa = 0.99999 + 1e-9 * (double)(a & 0xff), fb = 1e-3 + 1e-9 * (double)(b & 0xff);
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) {
+        d[k] = 1.0 + threadIdx.x + k;
+        x[k] = ((unsigned long long)(a + k) << 32) | (threadIdx.x + k);
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 32 / (DF + WIDE); u++) {
+#pragma unroll
+            for (int k = 0; k < DF; k++)
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k % CHAINS]) : "d"(fa), "d"(fb));
+#pragma unroll
+            for (int k = 0; k < WIDE; k++) x[k % CHAINS] = (unsigned long long)(uint32_t)x[k % CHAINS] * b + x[k % CHAINS];
+        }
+    }
+    const long long t1 = clock64();
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < CHAINS; k++) acc ^= x[k] ^ (unsigned long long)__double_as_longlong(d[k]);
+    if (acc == 0x12345ull) sink[0] = (uint32_t)acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 }  // namespace
 
 cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double* clock_mhz,
@@ -150,7 +185,10 @@ cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double*
         if (kind == 0) imad_lo_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
         else if (kind == 1) imad_wide_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
         else if (kind == 2) imad_chain_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
-        else imad_hi_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else if (kind == 3) imad_hi_kernel<<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else if (kind == 4) dfma_mix_kernel<8, 0><<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else if (kind == 5) dfma_mix_kernel<8, 8><<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
+        else dfma_mix_kernel<8, 4><<<blocks, threads, 0, st>>>(sink, 0x9e3779b1u, 0x7f4a7c15u, cyc);
         cudaEventRecord(e1, st);
         e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) break;
@@ -167,8 +205,11 @@ cudaError_t launch_imad_peak(int kind, int sm_count, double* imad_per_s, double*
     cudaFree(sink);
     cudaFree(cyc);
     if (e != cudaSuccess) return e;
-    // instructions per thread per iteration: 32 everywhere (4 x 8 chains, or 2 x 4 chains x 4 wide)
-    const double ops = (double)blocks * threads * (double)ITERS * 32 * ((kind == 1 || kind == 2) ? 2.0 : 1.0);
+    // instructions per thread per iteration: 32 (4 x 8 chains, or 2 x 4 chains x 4 wide), 24 for kind 6
+    // (2 x (8 DFMA + 4 wide)); kinds 1, 2 count a wide multiply as two IMAD-equivalents, kinds 4-6
+    // report plain instructions per second (DFMA and wide multiplies alike)
+    const double ops = (double)blocks * threads * (double)ITERS * (kind == 6 ? 24 : 32) *
+                       ((kind == 1 || kind == 2) ? 2.0 : 1.0);
     *imad_per_s = ops / (best_ms * 1e-3);
     // SM cycles one resident block spent in the loop over the wall time of the
     // launch: the SM clock under this load, to first order (the grid is exactly

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "poseidon.cuh"
 #include "fr29.cuh"
+#include "kara.cuh"
 using namespace inf;
 
 constexpr int ITERS = 2000;
@@ -73,6 +74,40 @@ __global__ void __launch_bounds__(128, 4) k_dot29(uint32_t* out, const uint32_t*
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// Karatsuba variants (kara.cuh): plain product and the 3-term dot
+__global__ void __launch_bounds__(128, 4) k_mulkara(uint32_t* out, const uint32_t* in) {
+    uint32_t x[8], y[8], z[8], ys[5];
+    for (int k = 0; k < 8; k++) { x[k] = in[k] + threadIdx.x; y[k] = in[8 + k]; z[k] = in[16 + k] ^ threadIdx.x; }
+    x[7] &= 0x1fffffff; y[7] &= 0x1fffffff; z[7] &= 0x1fffffff;
+    half_sums(ys, y, 1);
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[8], u[8];
+        dot_kara<1, 8>(t, x, y, ys);
+        dot_kara<1, 8>(u, z, y, ys);
+        for (int k = 0; k < 8; k++) { x[k] = t[k]; z[k] = u[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 8; k++) acc ^= x[k] ^ z[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void __launch_bounds__(128, 4) k_dotkara(uint32_t* out, const uint32_t* in) {
+    uint32_t s[3][8], b[24], bs[15];
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 8; k++) { s[j][k] = in[8 * j + k] + threadIdx.x; b[8 * j + k] = in[32 + 8 * j + k]; }
+    for (int j = 0; j < 3; j++) { s[j][7] &= 0x1fffffff; b[8 * j + 7] &= 0x1fffffff; }
+    half_sums(bs, b, 3);
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+        uint32_t t[8];
+        dot_kara<3, 8>(t, &s[0][0], b, bs);
+        csub2p(t);
+        for (int k = 0; k < 8; k++) { s[0][k] = s[1][k]; s[1][k] = s[2][k]; s[2][k] = t[k]; }
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < 8; k++) acc ^= s[0][k] ^ s[1][k] ^ s[2][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <typename F> float time_it(F f) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); cudaDeviceSynchronize();
@@ -94,6 +129,8 @@ int main(int argc, char** argv) {
         k_mul29<true><<<blocks, threads>>>(out, in);
         k_dot32<<<blocks, threads>>>(out, in);
         k_dot29<<<blocks, threads>>>(out, in);
+        k_mulkara<<<blocks, threads>>>(out, in);
+        k_dotkara<<<blocks, threads>>>(out, in);
         cudaDeviceSynchronize();
         printf("%s\n", cudaGetErrorString(cudaGetLastError()));
         return 0;
@@ -108,6 +145,8 @@ int main(int argc, char** argv) {
         ms = time_it([&] { k_mul29<true><<<blocks, threads>>>(out, in); });  printf("blocks/SM-wave %d: sqr29  %8.2f G sqr/s\n", bps, 2 * n / ms / 1e6);
         ms = time_it([&] { k_dot32<<<blocks, threads>>>(out, in); });        printf("blocks/SM-wave %d: dot3_32 %8.2f G dot/s\n", bps, n / ms / 1e6);
         ms = time_it([&] { k_dot29<<<blocks, threads>>>(out, in); });        printf("blocks/SM-wave %d: dot3_29 %8.2f G dot/s\n", bps, n / ms / 1e6);
+        ms = time_it([&] { k_mulkara<<<blocks, threads>>>(out, in); });      printf("blocks/SM-wave %d: mulkara %8.2f G mul/s\n", bps, 2 * n / ms / 1e6);
+        ms = time_it([&] { k_dotkara<<<blocks, threads>>>(out, in); });      printf("blocks/SM-wave %d: dot3kara %8.2f G dot/s\n", bps, n / ms / 1e6);
         cudaFree(out);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
