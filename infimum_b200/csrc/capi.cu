@@ -261,16 +261,27 @@ int rows_pipeline(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* 
     if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], n_stage * 32))) return rc;
     char* s0 = (char*)ctx->io[0];
     char* s1 = s0 + n_stage * row0;
+    // The read-back of chunk k is queued two chunks late: with pageable caller
+    // buffers a device-to-host copy blocks the calling thread until the chunk's
+    // kernel is done, which would serialise the whole loop; this way the thread
+    // is staging the upload of chunk k+2 while chunk k is being hashed.
+    const uint64_t lag = 2;
     for (uint64_t base = 0; base < n; base += super) {
         const uint64_t m = std::min<uint64_t>(super, n - base);
-        int k = 0;
-        for (uint64_t off = 0; off < m; off += chunk, k++) {
-            const uint64_t c = std::min<uint64_t>(chunk, m - off);
-            cudaStream_t st = ctx->pipe[k % 3];
-            CU(cudaMemcpyAsync(s0 + off * row0, in0 + (base + off) * row0, c * row0, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(s1 + off * row1, in1 + (base + off) * row1, c * row1, cudaMemcpyHostToDevice, st));
-            CU(launch(s0 + off * row0, s1 + off * row1, (char*)ctx->io[1] + off * 32, c, st));
-            CU(cudaMemcpyAsync(out + (base + off) * 32, (char*)ctx->io[1] + off * 32, c * 32, cudaMemcpyDeviceToHost, st));
+        const uint64_t n_chunks = (m + chunk - 1) / chunk;
+        for (uint64_t k = 0; k < n_chunks + lag; k++) {
+            if (k < n_chunks) {
+                const uint64_t off = k * chunk, c = std::min<uint64_t>(chunk, m - off);
+                cudaStream_t st = ctx->pipe[k % 3];
+                CU(cudaMemcpyAsync(s0 + off * row0, in0 + (base + off) * row0, c * row0, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(s1 + off * row1, in1 + (base + off) * row1, c * row1, cudaMemcpyHostToDevice, st));
+                CU(launch(s0 + off * row0, s1 + off * row1, (char*)ctx->io[1] + off * 32, c, st));
+            }
+            if (k >= lag) {
+                const uint64_t off = (k - lag) * chunk, c = std::min<uint64_t>(chunk, m - off);
+                CU(cudaMemcpyAsync(out + (base + off) * 32, (char*)ctx->io[1] + off * 32, c * 32, cudaMemcpyDeviceToHost,
+                                   ctx->pipe[(k - lag) % 3]));
+            }
         }
         for (int i = 0; i < 3; i++) CU(cudaStreamSynchronize(ctx->pipe[i]));
     }
@@ -428,19 +439,27 @@ static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, cons
     const uint64_t n_stage = std::min<uint64_t>(n, super);
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_stage * in_row))) return rc;
     if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], n_stage * 32))) return rc;
+    const uint64_t lag = 2;     // read-back queued two chunks late, see rows_pipeline
     for (uint64_t base = 0; base < n; base += super) {
         const uint64_t m = std::min<uint64_t>(super, n - base);
-        int k = 0;
-        for (uint64_t off = 0; off < m; off += chunk, k++) {
-            const uint64_t c = std::min<uint64_t>(chunk, m - off);
-            cudaStream_t st = (m <= chunk) ? ctx->stream : ctx->pipe[k % 3];
-            char* d_in = (char*)ctx->io[0] + off * in_row;
-            char* d_out = (char*)ctx->io[1] + off * 32;
-            CU(cudaMemcpyAsync(d_in, in + (base + off) * in_row, c * in_row, cudaMemcpyHostToDevice, st));
-            if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, d_out, st, dense))) return rc;
-            CU(cudaMemcpyAsync(out + (base + off) * 32, d_out, c * 32, cudaMemcpyDeviceToHost, st));
+        const uint64_t n_chunks = (m + chunk - 1) / chunk;
+        const bool single = n_chunks == 1;
+        for (uint64_t k = 0; k < n_chunks + lag; k++) {
+            if (k < n_chunks) {
+                const uint64_t off = k * chunk, c = std::min<uint64_t>(chunk, m - off);
+                cudaStream_t st = single ? ctx->stream : ctx->pipe[k % 3];
+                char* d_in = (char*)ctx->io[0] + off * in_row;
+                CU(cudaMemcpyAsync(d_in, in + (base + off) * in_row, c * in_row, cudaMemcpyHostToDevice, st));
+                if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, (char*)ctx->io[1] + off * 32, st, dense)))
+                    return rc;
+            }
+            if (k >= lag) {
+                const uint64_t off = (k - lag) * chunk, c = std::min<uint64_t>(chunk, m - off);
+                CU(cudaMemcpyAsync(out + (base + off) * 32, (char*)ctx->io[1] + off * 32, c * 32, cudaMemcpyDeviceToHost,
+                                   single ? ctx->stream : ctx->pipe[(k - lag) % 3]));
+            }
         }
-        if (m <= chunk) {
+        if (single) {
             CU(cudaStreamSynchronize(ctx->stream));
         } else {
             for (int i = 0; i < 3; i++) CU(cudaStreamSynchronize(ctx->pipe[i]));

@@ -48,6 +48,7 @@ def test_maximum_size_2_28_leaves():
     a, b, h = C.c_uint32(), C.c_uint32(), C.c_int()
 
     def merge(arity, depth):
+        torch.cuda.synchronize()        # the leaves were written on torch's stream, the merge runs on the context's
         rc = ctx.lib.inf_tree_merge_dev(ctx.handle, arity, depth, 0, 1, lv.data_ptr(), n, root, C.byref(a), C.byref(b),
                                         C.byref(h), None)
         assert rc in (0, 2), rc

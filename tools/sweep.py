@@ -59,6 +59,7 @@ def main():
                                                 C.byref(b), C.byref(h), stream.cuda_stream)
                 assert rc in (0, 2), rc
 
+            torch.cuda.synchronize(dev)      # leaves were generated on torch's default stream
             run()
             torch.cuda.synchronize(dev)
             best = None
