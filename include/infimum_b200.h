@@ -96,6 +96,21 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
                                 const uint8_t* domain_tag /* host */, const void* d_in, uint64_t n,
                                 void* d_out, void* stream);
 
+/* Poseidon::new(params) (poseidon.rs:47-71, 105-108): the same hash with
+ * caller-supplied PoseidonParameters instead of the circom tables.
+ *   ark   (full_rounds + partial_rounds) * width elements, index round*width + i
+ *         (poseidon.rs:126)
+ *   mds   width * width elements, row-major: mds[i][j] at i*width + j (poseidon.rs:153)
+ * both 32-byte big-endian (values >= p are reduced).  Rounds 0 .. full_rounds/2 - 1
+ * and the last full_rounds - full_rounds/2 are full, the partial_rounds in between
+ * apply x^alpha to state[0] only (poseidon.rs:184-203).  width 2..13 (else
+ * INVALID_WIDTH_CIRCOM); at most 4096 rounds.  Runs the reference schedule
+ * literally (the dense kernel): correct for any parameters, not tuned. */
+int inf_poseidon_hash_batch_params(inf_ctx* ctx, uint32_t width, uint32_t full_rounds,
+                                   uint32_t partial_rounds, uint64_t alpha, const uint8_t* ark,
+                                   const uint8_t* mds, uint32_t flags, const uint8_t* domain_tag,
+                                   const uint8_t* in, uint64_t n, uint8_t* out);
+
 /* Byte-slice front end with the reference's length checks, one hash:
  * inputs[i] has lens[i] bytes.  Empty -> EMPTY_INPUT, any other length than 32
  * -> INVALID_INPUT_LENGTH (validate_bytes_length + bytes_to_prime_field_element,

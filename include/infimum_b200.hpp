@@ -190,11 +190,35 @@ inline PoseidonError poseidon_error_from(int rc, size_t inputs, size_t width) {
 }
 
 // ---- Poseidon -----------------------------------------------------------------------------
+// PoseidonParameters (poseidon.rs:33-71): ark indexed round*width + i, mds[i][j] row i column j.
+struct PoseidonParameters {
+    std::vector<Fr> ark;
+    std::vector<std::vector<Fr>> mds;
+    size_t full_rounds = 0, partial_rounds = 0, width = 0;
+    uint64_t alpha = 5;
+    PoseidonParameters(std::vector<Fr> ark_, std::vector<std::vector<Fr>> mds_, size_t full_rounds_,
+                       size_t partial_rounds_, size_t width_, uint64_t alpha_)
+        : ark(std::move(ark_)), mds(std::move(mds_)), full_rounds(full_rounds_), partial_rounds(partial_rounds_),
+          width(width_), alpha(alpha_) {}
+};
+
 class Poseidon {
     size_t width_;
     Fr domain_tag_;
     Context* ctx_;
+    // set when built from caller-supplied parameters (Poseidon::new(params), poseidon.rs:105-108)
+    std::vector<uint8_t> ark_, mds_;
+    size_t full_rounds_ = 0, partial_rounds_ = 0;
+    uint64_t alpha_ = 5;
+    bool custom_ = false;
     Poseidon(size_t width, Fr tag, Context* ctx) : width_(width), domain_tag_(tag), ctx_(ctx) {}
+    int run(uint32_t flags, const uint8_t* tag, const uint8_t* rows, uint64_t n, uint8_t* out) const {
+        if (custom_)
+            return inf_poseidon_hash_batch_params(ctx_->get(), (uint32_t)width_, (uint32_t)full_rounds_,
+                                                  (uint32_t)partial_rounds_, alpha_, ark_.data(), mds_.data(), flags,
+                                                  tag, rows, n, out);
+        return inf_poseidon_hash_batch(ctx_->get(), (uint32_t)(width_ - 1), flags, tag, rows, n, out);
+    }
     const uint8_t* tag_ptr(HashBytes& scratch, bool le) const {
         if (domain_tag_.is_zero()) return nullptr;
         scratch = le ? domain_tag_.to_bytes_le() : domain_tag_.be;
@@ -210,6 +234,26 @@ public:
         if (width > MAX_X5_LEN || width < 2) return PoseidonError::invalid_width_circom(width);
         return Poseidon(width, domain_tag, ctx ? ctx : &Context::global());
     }
+    // Poseidon::new(params) / with_domain_tag(params, tag)  (poseidon.rs:105-118; `new` is a keyword here)
+    static Result<Poseidon, PoseidonError> with_params(const PoseidonParameters& params, Fr domain_tag = Fr::zero(),
+                                                       Context* ctx = nullptr) {
+        if (params.width > MAX_X5_LEN || params.width < 2) return PoseidonError::invalid_width_circom(params.width);
+        if (params.ark.size() != (params.full_rounds + params.partial_rounds) * params.width ||
+            params.mds.size() != params.width)
+            throw std::invalid_argument("PoseidonParameters: ark / mds sizes do not match the round counts and width");
+        Poseidon h(params.width, domain_tag, ctx ? ctx : &Context::global());
+        h.custom_ = true;
+        h.full_rounds_ = params.full_rounds;
+        h.partial_rounds_ = params.partial_rounds;
+        h.alpha_ = params.alpha;
+        for (const Fr& x : params.ark) h.ark_.insert(h.ark_.end(), x.be.begin(), x.be.end());
+        for (const auto& row : params.mds) {
+            if (row.size() != params.width) throw std::invalid_argument("PoseidonParameters: mds is not square");
+            for (const Fr& x : row) h.mds_.insert(h.mds_.end(), x.be.begin(), x.be.end());
+        }
+        h.ark_.resize(h.ark_.size() + 32);          // never hand the library a null pointer for zero rounds
+        return h;
+    }
     size_t width() const { return width_; }
 
     // PoseidonHasher::hash
@@ -219,8 +263,7 @@ public:
         for (size_t i = 0; i < inputs.size(); i++) memcpy(&buf[32 * i], inputs[i].be.data(), 32);
         Fr out;
         HashBytes tag;
-        int rc = inf_poseidon_hash_batch(ctx_->get(), (uint32_t)inputs.size(), 0, tag_ptr(tag, false), buf.data(),
-                                         1, out.be.data());
+        int rc = run(0, tag_ptr(tag, false), buf.data(), 1, out.be.data());
         if (rc) return poseidon_error_from(rc, inputs.size(), width_);
         return out;
     }
@@ -229,8 +272,7 @@ public:
     Result<std::vector<HashBytes>, PoseidonError> hash_batch(const uint8_t* rows, uint64_t n) {
         std::vector<HashBytes> out(n);
         HashBytes tag;
-        int rc = inf_poseidon_hash_batch(ctx_->get(), (uint32_t)(width_ - 1), 0, tag_ptr(tag, false), rows, n,
-                                         n ? out[0].data() : nullptr);
+        int rc = run(0, tag_ptr(tag, false), rows, n, n ? out[0].data() : nullptr);
         if (rc) return poseidon_error_from(rc, width_ - 1, width_);
         return out;
     }
@@ -250,10 +292,17 @@ private:
             if (s.second != HASH_LEN) return PoseidonError::invalid_input_length(s.second);
         }
         if (inputs.size() != width_ - 1) return PoseidonError::invalid_number_of_inputs(inputs.size(), width_);
+        HashBytes out, tag;
+        if (custom_) {
+            std::vector<uint8_t> buf;
+            for (const Slice& s : inputs) buf.insert(buf.end(), s.first, s.first + 32);
+            int rc = run(flags, tag_ptr(tag, flags != 0), buf.data(), 1, out.data());
+            if (rc) return poseidon_error_from(rc, inputs.size(), width_);
+            return out;
+        }
         std::vector<const uint8_t*> ptrs;
         std::vector<size_t> lens;
         for (const Slice& s : inputs) { ptrs.push_back(s.first); lens.push_back(s.second); }
-        HashBytes out, tag;
         int rc = inf_poseidon_hash_bytes(ctx_->get(), flags, tag_ptr(tag, flags != 0), ptrs.data(), lens.data(),
                                          (uint32_t)inputs.size(), out.data());
         if (rc) return poseidon_error_from(rc, inputs.size(), width_);

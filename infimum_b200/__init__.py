@@ -8,7 +8,7 @@ reference interface over that ABI.  CUDA only: there is no CPU fallback.
 """
 from .errors import DeviceError, MerkleTreeError, PoseidonError
 from .context import Context, get_context
-from .hasher import HASH_LEN, MAX_X5_LEN, MODULUS, Poseidon
+from .hasher import HASH_LEN, MAX_X5_LEN, MODULUS, Poseidon, PoseidonParameters
 from .leaves import interaction_leaves, registration_leaves
 from .paths import RetainedTree, compute_merkle_root_from_path, merkle_roots_from_paths, verify_outcome
 from .poll import Commitment, Poll, PollConfig
@@ -16,7 +16,7 @@ from .tree import (PollStateTree, empty_ballot_roots, get_merkle_zeroes, merge_i
                    merge_registrations, new_interaction_tree, new_registration_tree)
 
 __all__ = [
-    "Context", "get_context", "Poseidon", "PollStateTree", "PoseidonError", "MerkleTreeError",
+    "Context", "get_context", "Poseidon", "PoseidonParameters", "PollStateTree", "PoseidonError", "MerkleTreeError",
     "DeviceError", "MODULUS", "HASH_LEN", "MAX_X5_LEN", "get_merkle_zeroes", "empty_ballot_roots",
     "merge_registrations", "merge_interactions", "new_registration_tree", "new_interaction_tree",
     "registration_leaves", "interaction_leaves", "Poll", "PollConfig", "Commitment",

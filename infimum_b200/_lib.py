@@ -43,7 +43,7 @@ EXPORTS = [
     "inf_tree_destroy", "inf_merkle_roots_from_paths", "inf_multi_init", "inf_multi_destroy",
     "inf_multi_device_count", "inf_multi_tree_merge", "inf_multi_poseidon_hash_batch", "inf_merge_registrations",
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
-    "inf_measure_imad_peak",
+    "inf_measure_imad_peak", "inf_poseidon_hash_batch_params",
 ]
 
 _lib = None
@@ -79,6 +79,9 @@ def load() -> C.CDLL:
     lib.inf_poseidon_hash_batch.restype = C.c_int
     lib.inf_poseidon_hash_batch_dense.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp]
     lib.inf_poseidon_hash_batch_dense.restype = C.c_int
+    lib.inf_poseidon_hash_batch_params.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, C.c_uint32,
+                                                   vp, vp, C.c_uint64, vp]
+    lib.inf_poseidon_hash_batch_params.restype = C.c_int
     lib.inf_poseidon_hash_batch_dev.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, vp]
     lib.inf_poseidon_hash_batch_dev.restype = C.c_int
     lib.inf_poseidon_hash_bytes.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),

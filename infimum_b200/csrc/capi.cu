@@ -132,12 +132,23 @@ uint64_t pow_sat(uint64_t a, uint32_t e) {
     return (uint64_t)r;
 }
 
+// Caller-supplied PoseidonParameters (Poseidon::new, poseidon.rs:47-71, 105-108), table on the device.
+struct CustomParams {
+    const uint32_t* d_tbl;
+    int full_rounds, partial_rounds;
+    uint64_t alpha;
+};
+
 int hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
-                   const void* d_in, uint64_t n, void* d_out, cudaStream_t st, bool dense) {
+                   const void* d_in, uint64_t n, void* d_out, cudaStream_t st, bool dense,
+                   const CustomParams* custom = nullptr) {
     const uint32_t t = n_inputs + 1;
     const bool le = flags & INF_FLAG_LITTLE_ENDIAN;
     const TagArg ta = make_tag(tag);
-    if (!dense && t <= 8) {
+    if (custom) {
+        CU(launch_hash_dense_params((int)t, custom->full_rounds, custom->partial_rounds, custom->alpha, custom->d_tbl,
+                                    d_in, d_out, n, ta, le, st));
+    } else if (!dense && t <= 8) {
         CU(hashers[t](d_in, d_out, n, ta, le, st));
     } else {
         CU(launch_hash_dense((int)t, ctx->d_dense[t], d_in, d_out, n, ta, le, st));
@@ -427,7 +438,8 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
 // host buffers the copies of one chunk hide behind the hashing of another (the
 // path is compute-bound: ~8 ns of hashing per 96 bytes moved).
 static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
-                           const uint8_t* in, uint64_t n, uint8_t* out, bool dense) {
+                           const uint8_t* in, uint64_t n, uint8_t* out, bool dense,
+                           const CustomParams* custom = nullptr) {
     int rc = check_hash_args(ctx, n_inputs, in, n, out);
     if (rc) return rc;
     if (n == 0) return INF_OK;
@@ -450,7 +462,8 @@ static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, cons
                 cudaStream_t st = single ? ctx->stream : ctx->pipe[k % 3];
                 char* d_in = (char*)ctx->io[0] + off * in_row;
                 CU(cudaMemcpyAsync(d_in, in + (base + off) * in_row, c * in_row, cudaMemcpyHostToDevice, st));
-                if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, (char*)ctx->io[1] + off * 32, st, dense)))
+                if ((rc = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, (char*)ctx->io[1] + off * 32, st, dense,
+                                         custom)))
                     return rc;
             }
             if (k >= lag) {
@@ -478,6 +491,40 @@ int inf_poseidon_hash_batch_dense(inf_ctx* ctx, uint32_t n_inputs, uint32_t flag
                                   const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
                                   uint8_t* out) {
     return hash_batch_host(ctx, n_inputs, flags, domain_tag, in, n, out, true);
+}
+
+int inf_poseidon_hash_batch_params(inf_ctx* ctx, uint32_t width, uint32_t full_rounds,
+                                   uint32_t partial_rounds, uint64_t alpha, const uint8_t* ark,
+                                   const uint8_t* mds, uint32_t flags, const uint8_t* domain_tag,
+                                   const uint8_t* in, uint64_t n, uint8_t* out) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (width < 2 || width > 13) return INF_ERR_INVALID_WIDTH_CIRCOM;
+    const uint64_t rounds = (uint64_t)full_rounds + partial_rounds;
+    if (rounds > 4096) return INF_ERR_BAD_DEPTH;
+    if (!mds || (rounds && !ark)) return INF_ERR_NULL_POINTER;
+    int rc = check_hash_args(ctx, width - 1, in, n, out);
+    if (rc) return rc;
+    if (n == 0) return INF_OK;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    // the table the dense kernel reads: [ark rounds*width][mds width*width], Montgomery form
+    const size_t n_ark = (size_t)rounds * width, n_el = n_ark + (size_t)width * width;
+    std::vector<uint32_t> tbl(n_el * 8);
+    for (size_t k = 0; k < n_el; k++) {
+        const uint8_t* src = k < n_ark ? ark + 32 * k : mds + 32 * (k - n_ark);
+        host::to_limbs32(host::to_mont(host::reduce256(host::from_be_bytes(src))), &tbl[8 * k]);
+    }
+    uint32_t* d_tbl = nullptr;
+    CU(cudaMalloc((void**)&d_tbl, tbl.size() * 4));
+    cudaError_t e = cudaMemcpy(d_tbl, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_tbl);
+        return cuda_fail(ctx, e, "upload custom parameters");
+    }
+    const CustomParams cp = {d_tbl, (int)full_rounds, (int)partial_rounds, alpha};
+    rc = hash_batch_host(ctx, width - 1, flags, domain_tag, in, n, out, true, &cp);
+    cudaFree(d_tbl);
+    return rc;
 }
 
 int inf_poseidon_hash_bytes(inf_ctx* ctx, uint32_t flags, const uint8_t* domain_tag,

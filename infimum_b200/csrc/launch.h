@@ -58,6 +58,9 @@ cudaError_t launch_gather_paths(const void* const* d_level_ptrs /* device array 
                                 cudaStream_t st);
 
 // Generic dense kernel (any width 2..13), dense_generic.cu
+cudaError_t launch_hash_dense_params(int t, int full_rounds, int rp, uint64_t alpha, const uint32_t* d_tbl,
+                                     const void* d_in, void* d_out, uint64_t n, const TagArg& tag, bool le,
+                                     cudaStream_t st);
 cudaError_t launch_hash_dense(int t, const uint32_t* d_tbl, const void* d_in, void* d_out,
                               uint64_t n, const TagArg& tag, bool le, cudaStream_t st);
 

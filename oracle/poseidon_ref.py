@@ -154,6 +154,25 @@ def poseidon_permute_hash(inputs: Sequence[int], domain_tag: int = 0) -> int:
     return state[0]
 
 
+def poseidon_hash_with_params(ark: Sequence[int], mds: Sequence[Sequence[int]], full_rounds: int, partial_rounds: int,
+                              width: int, alpha: int, inputs: Sequence[int], domain_tag: int = 0) -> int:
+    """PoseidonHasher::hash for a hasher built with Poseidon::new(PoseidonParameters::new(ark, mds,
+    full_rounds, partial_rounds, width, alpha)) (poseidon.rs:47-71, 105-108, 162-208): the same
+    schedule with caller-supplied constants, round counts and S-box exponent."""
+    if len(inputs) != width - 1:
+        raise PoseidonError("InvalidNumberOfInputs", inputs=len(inputs), max_limit=width - 1, width=width)
+    state = [domain_tag % P] + [x % P for x in inputs]
+    half = full_rounds // 2                                                     # :183
+    for rnd in range(full_rounds + partial_rounds):
+        state = [(s + ark[rnd * width + i]) % P for i, s in enumerate(state)]
+        if rnd < half or rnd >= half + partial_rounds:
+            state = [pow(s, alpha, P) for s in state]
+        else:
+            state[0] = pow(state[0], alpha, P)
+        state = [sum(s * mds[i][j] for j, s in enumerate(state)) % P for i in range(width)]
+    return state[0]
+
+
 class Poseidon:
     """Mirror of `Poseidon<Fr>` built with new_circom / with_domain_tag_circom."""
 

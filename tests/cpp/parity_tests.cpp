@@ -119,6 +119,35 @@ static void circomlibjs_compat_1_to_12_inputs() {
     }
 }
 
+// Poseidon::new(params) with the parameters.rs tables (fetched from the library's own Grain
+// regeneration) must be new_circom: pinned by the circomlibjs vectors.
+static void custom_parameters_equal_new_circom() {
+    HashBytes one = be32(1);
+    for (size_t n_inputs : {1u, 2u, 5u, 12u}) {
+        const size_t t = n_inputs + 1;
+        static const int RP[12] = {56, 57, 56, 60, 60, 63, 64, 63, 60, 66, 60, 65};
+        const size_t n_ark = (8 + RP[t - 2]) * t, n_el = n_ark + t * t;
+        std::vector<uint32_t> w(n_el * 8);
+        CHECK(inf_debug_dense_params((uint32_t)t, w.data(), w.size()) == (int)n_el);
+        auto el = [&](size_t k) {
+            Fr r;
+            for (int i = 0; i < 8; i++)
+                for (int b = 0; b < 4; b++) r.be[31 - (4 * i + b)] = (uint8_t)(w[8 * k + i] >> (8 * b));
+            return r;
+        };
+        std::vector<Fr> ark;
+        for (size_t k = 0; k < n_ark; k++) ark.push_back(el(k));
+        std::vector<std::vector<Fr>> mds(t);
+        for (size_t i = 0; i < t; i++)
+            for (size_t j = 0; j < t; j++) mds[i].push_back(el(n_ark + i * t + j));
+        auto hasher = Poseidon::with_params(PoseidonParameters(ark, mds, 8, RP[t - 2], t, 5)).unwrap();
+        std::vector<Poseidon::Slice> ones(n_inputs, {one.data(), 32});
+        CHECK(hasher.hash_bytes_be(ones).unwrap() == HB(G_CIRCOMLIBJS[n_inputs - 1]));
+        CHECK(hasher.hash(std::vector<Fr>(n_inputs, Fr::one())).unwrap().be == HB(G_CIRCOMLIBJS[n_inputs - 1]));
+        CHECK(hasher.hash({}).is_err());
+    }
+}
+
 // ---- pallet/src/poll/zeroes.rs -----------------------------------------------------------------
 static void zero_tables() {
     auto b = get_merkle_zeroes(2), q = get_merkle_zeroes(5), other = get_merkle_zeroes(7);
@@ -291,7 +320,8 @@ int main() {
     const T tests[] = {
         {"fr_one", fr_one}, {"bytes_ones_twos", bytes_ones_twos}, {"with_domain_tag", with_domain_tag},
         {"fr_one_two", fr_one_two}, {"random_input", random_input}, {"empty_input", empty_input},
-        {"circomlibjs_compat_1_to_12_inputs", circomlibjs_compat_1_to_12_inputs}, {"zero_tables", zero_tables},
+        {"circomlibjs_compat_1_to_12_inputs", circomlibjs_compat_1_to_12_inputs},
+        {"custom_parameters_equal_new_circom", custom_parameters_equal_new_circom}, {"zero_tables", zero_tables},
         {"merge_registration_state_success", merge_registration_state_success},
         {"merge_interaction_state_success", merge_interaction_state_success},
         {"process_messages_public_signals", process_messages_public_signals},

@@ -313,6 +313,40 @@ def test_full_size_properties_2_24(ib):
     assert whole == c_oracle.hash_one([left, right])
 
 
+# ---- Poseidon::new(params): caller-supplied PoseidonParameters (poseidon.rs:47-71, 105-108) ----
+def test_custom_parameters_equal_new_circom_for_the_circom_tables(ib, golden):
+    for n_inputs in (1, 2, 5, 12):
+        ark, mds, rf, rp = O.poseidon_parameters(n_inputs + 1)
+        h = ib.Poseidon.new(ib.PoseidonParameters(ark, mds, rf, rp, n_inputs + 1, 5))
+        assert h.hash([1] * n_inputs) == int(golden["circomlibjs_ones"][n_inputs - 1], 16)
+    ark, mds, rf, rp = O.poseidon_parameters(3)
+    h = ib.Poseidon.new(ib.PoseidonParameters(ark, mds, rf, rp, 3, 5))
+    a, b = H(golden["random_input"]["inputs_be"][0]), H(golden["random_input"]["inputs_be"][1])
+    assert h.hash_bytes_le([a[::-1], b[::-1]]) == H(golden["random_input"]["expected_le"])
+    with pytest.raises(ib.PoseidonError) as e:
+        h.hash([1])
+    assert e.value.kind == "InvalidNumberOfInputs"
+
+
+@pytest.mark.parametrize("width,full_rounds,partial_rounds,alpha", [(4, 7, 3, 3), (2, 2, 0, 7), (13, 4, 2, 5),
+                                                                    (3, 0, 5, 17), (5, 6, 9, 1), (3, 0, 0, 5)])
+def test_custom_parameters_vs_oracle(ib, width, full_rounds, partial_rounds, alpha):
+    """Arbitrary constants, odd full_rounds (the second half gets the extra round,
+    poseidon.rs:183-203), other S-box exponents, with and without a domain tag."""
+    rng = random.Random(width * 1000 + full_rounds * 10 + alpha)
+    ark = [rng.randrange(P) for _ in range((full_rounds + partial_rounds) * width)]
+    mds = [[rng.randrange(P) for _ in range(width)] for _ in range(width)]
+    n = 37
+    rows = [[rng.choice(EDGE_VALUES + [rng.randrange(P)]) for _ in range(width - 1)] for _ in range(n)]
+    buf = b"".join(be(x % (1 << 256)) for r in rows for x in r)
+    for tag in (0, 12345):
+        h = ib.Poseidon.with_domain_tag(ib.PoseidonParameters(ark, mds, full_rounds, partial_rounds, width, alpha), tag)
+        got = h.hash_batch(buf, n)
+        for i, r in enumerate(rows):
+            exp = O.poseidon_hash_with_params(ark, mds, full_rounds, partial_rounds, width, alpha, r, tag)
+            assert got[i].tobytes() == be(exp), (i, tag)
+
+
 # ---- frontier (`PollStateTree.hashes` before the merge, state.rs:85-86) -----------------------
 @pytest.mark.parametrize("arity,full_depth,blank", [(2, 11, True), (5, 5, False), (2, 11, False), (5, 5, True)])
 def test_frontier_equals_insert_cascade(ib, arity, full_depth, blank):

@@ -207,3 +207,13 @@ def test_merkle_path_roundtrip():
         for idx in (0, 1, 4, 5, 24, 37):
             path = O.merkle_path(levels, arity, idx)
             assert O.compute_merkle_root_from_path(depth, idx, leaves[idx], path, arity) == root
+
+
+def test_custom_parameters_restatement_agrees_with_the_circom_hasher():
+    """Poseidon::new(params) (poseidon.rs:105-108) with the parameters.rs tables must be
+    new_circom (poseidon.rs:304-326): pins the generic-parameter oracle to the same KATs."""
+    for t in (2, 3, 6, 13):
+        ark, mds, rf, rp = O.poseidon_parameters(t)
+        ins = [(7 * i + 1) % O.P for i in range(t - 1)]
+        assert O.poseidon_hash_with_params(ark, mds, rf, rp, t, 5, ins) == O.poseidon_permute_hash(ins)
+        assert O.poseidon_hash_with_params(ark, mds, rf, rp, t, 5, ins, 9) == O.poseidon_permute_hash(ins, 9)
