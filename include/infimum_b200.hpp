@@ -451,6 +451,7 @@ inline PollStateTree new_interaction_tree(uint8_t interaction_depth, Context* ct
 // ---- provider.rs:289-327 ------------------------------------------------------------------------------
 struct Commitment {                                      // coordinator.rs (subset used here)
     std::pair<uint32_t, HashBytes> process{0, HashBytes{}};
+    std::pair<uint32_t, HashBytes> tally{0, HashBytes{}};
     uint32_t expected_process = 0, expected_tally = 0;
 };
 
@@ -517,10 +518,19 @@ interaction_leaves(const std::vector<PublicKey>& keys, const std::vector<PollInt
 // The slice of `Poll` that drives the hot path: the two trees, the commitment,
 // and register_participant / consume_interaction / merge_* with the reference's
 // signatures (provider.rs:218-327).  Leaves are hashed in bulk at merge time.
+// What prepare_public_inputs returns, without the verify key (Groth16 is out of scope):
+// which circuit the inputs are for, the inputs, and the commitment the proof would install.
+struct PublicInputs {
+    bool process = true;                 // false: tally circuit
+    std::vector<Fr> inputs;
+    Commitment commitment;
+};
+
 struct Poll {
     PollStateTree registrations, interactions;
     Commitment commitment;
     uint8_t process_subtree_depth = 0, tally_subtree_depth = 0;
+    uint64_t created_at = 0, signup_period = 0, voting_period = 0;      // poll.rs / config.rs, for get_voting_period_end
 
     Poll(uint8_t registration_depth, uint8_t interaction_depth, uint8_t process_subtree_depth_,
          uint8_t tally_subtree_depth_, Context* ctx = nullptr)
@@ -556,6 +566,52 @@ struct Poll {
         interactions = std::move(r.unwrap().first);
         commitment = r.unwrap().second;
         return std::nullopt;
+    }
+
+    uint64_t get_voting_period_end() const { return created_at + signup_period + voting_period; }   // provider.rs:355-358
+
+    // prepare_public_inputs (provider.rs:141-215); u32 arithmetic as in the reference
+    std::optional<PublicInputs> prepare_public_inputs(const PublicKey& coordinator_public_key,
+                                                      const HashBytes& new_commitment) const {
+        PublicInputs out;
+        uint32_t message_batch_size = 1;
+        for (int i = 0; i < process_subtree_depth; i++) message_batch_size *= interactions.arity;
+        uint32_t current_batch_index = interactions.count;
+        if (current_batch_index > 0) {
+            const uint32_t r = interactions.count % message_batch_size;
+            current_batch_index -= r == 0 ? message_batch_size : r;
+        }
+        uint32_t proof_index = commitment.process.first;
+        const uint32_t index_offset = proof_index * message_batch_size;
+        out.commitment = commitment;
+        if (index_offset <= current_batch_index) {
+            auto hasher = Poseidon::new_circom(2, ctx_);
+            if (hasher.is_err()) return std::nullopt;
+            auto h = hasher.unwrap().hash({Fr::from_be_bytes_mod_order(coordinator_public_key.x),
+                                           Fr::from_be_bytes_mod_order(coordinator_public_key.y)});
+            if (h.is_err() || !interactions.root) return std::nullopt;
+            current_batch_index -= index_offset;
+            uint32_t end_batch_index = current_batch_index + message_batch_size;
+            if (end_batch_index > interactions.count) end_batch_index = interactions.count;
+            out.inputs = {Fr::from(registrations.count + 1), Fr::from(get_voting_period_end()),
+                          Fr::from_be_bytes_mod_order(*interactions.root), Fr::from(registrations.depth),
+                          Fr::from(end_batch_index), Fr::from(current_batch_index), h.unwrap(),
+                          Fr::from_be_bytes_mod_order(commitment.process.second),
+                          Fr::from_be_bytes_mod_order(new_commitment)};
+            out.commitment.process = {proof_index + 1, new_commitment};
+            return out;
+        }
+        out.process = false;
+        proof_index = commitment.tally.first;
+        uint32_t batch_size = 1;
+        for (int i = 0; i < tally_subtree_depth; i++) batch_size *= registrations.arity;
+        current_batch_index = proof_index * batch_size;
+        if (current_batch_index >= registrations.count + 1) return std::nullopt;
+        out.inputs = {Fr::from_be_bytes_mod_order(commitment.process.second),
+                      Fr::from_be_bytes_mod_order(commitment.tally.second), Fr::from_be_bytes_mod_order(new_commitment),
+                      Fr::from(current_batch_index), Fr::from(registrations.count + 1)};
+        out.commitment.tally = {proof_index + 1, new_commitment};
+        return out;
     }
 
 private:

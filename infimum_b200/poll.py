@@ -5,6 +5,8 @@ path (pallet/src/poll/provider.rs, pallet/src/poll/state.rs:14-67):
     register_participant(public_key, timestamp)                provider.rs:218-241
     consume_interaction(public_key, data)                      provider.rs:243-287
     merge_registrations() / merge_interactions()               provider.rs:289-327
+    prepare_public_inputs(coordinator, new_commitment)         provider.rs:141-215
+    get_voting_period_end()                                    provider.rs:355-358
     registration_limit_reached / interaction_limit_reached     provider.rs:329-341
 
 Leaves are hashed in bulk on the GPU when they are needed (at merge time, or
@@ -38,12 +40,15 @@ class PollConfig:                       # config.rs, the fields this path reads
     interaction_depth: int
     process_subtree_depth: int
     tally_subtree_depth: int
+    signup_period: int = 0
+    voting_period: int = 0
 
 
 class Poll:
-    def __init__(self, config: PollConfig, ctx: Optional[Context] = None):
+    def __init__(self, config: PollConfig, ctx: Optional[Context] = None, created_at: int = 0):
         self.ctx = ctx or get_context()
         self.config = config
+        self.created_at = created_at
         self.registrations: PollStateTree = new_registration_tree(config.registration_depth, self.ctx)
         self.interactions: PollStateTree = new_interaction_tree(config.interaction_depth, self.ctx)
         self.commitment = Commitment()
@@ -102,3 +107,41 @@ class Poll:
                                                         self.config.tally_subtree_depth)
         self.commitment.expected_process, self.commitment.expected_tally = ep, et
         return self
+
+    def get_voting_period_end(self) -> int:                       # provider.rs:355-358
+        return self.created_at + self.config.signup_period + self.config.voting_period
+
+    def prepare_public_inputs(self, coordinator_public_key: Tuple[bytes, bytes], new_commitment: bytes):
+        """provider.rs:141-215 without the verify key: ("process" | "tally", the public
+        inputs as integers, the commitment the proof would install) or None."""
+        from .hasher import MODULUS, Poseidon
+        fr = lambda b: int.from_bytes(bytes(b), "big") % MODULUS      # Fr::from_be_bytes_mod_order
+        reg, it, c = self.registrations, self.interactions, self.commitment
+        message_batch_size = it.arity ** self.config.process_subtree_depth
+        current_batch_index = it.count
+        if current_batch_index > 0:
+            r = it.count % message_batch_size
+            current_batch_index -= message_batch_size if r == 0 else r
+        proof_index = c.process[0]
+        index_offset = proof_index * message_batch_size
+        if index_offset <= current_batch_index:
+            coord_hash = Poseidon.new_circom(2, self.ctx).hash([fr(coordinator_public_key[0]),
+                                                                fr(coordinator_public_key[1])])
+            if it.root is None:
+                return None
+            current_batch_index -= index_offset
+            end_batch_index = min(current_batch_index + message_batch_size, it.count)
+            inputs = [reg.count + 1, self.get_voting_period_end(), fr(it.root), reg.depth, end_batch_index,
+                      current_batch_index, coord_hash, fr(c.process[1]), fr(new_commitment)]
+            nxt = Commitment(process=(proof_index + 1, bytes(new_commitment)), tally=c.tally,
+                             expected_process=c.expected_process, expected_tally=c.expected_tally)
+            return "process", inputs, nxt
+        proof_index = c.tally[0]
+        batch_size = reg.arity ** self.config.tally_subtree_depth
+        current_batch_index = proof_index * batch_size
+        if current_batch_index >= reg.count + 1:
+            return None
+        inputs = [fr(c.process[1]), fr(c.tally[1]), fr(new_commitment), current_batch_index, reg.count + 1]
+        nxt = Commitment(process=c.process, tally=(proof_index + 1, bytes(new_commitment)),
+                         expected_process=c.expected_process, expected_tally=c.expected_tally)
+        return "tally", inputs, nxt

@@ -371,6 +371,39 @@ def merge_interactions(tree: PollStateTree, registrations_count: int,
     return tree, expected_process, expected_tally
 
 
+def prepare_public_inputs(registrations: PollStateTree, interactions: PollStateTree, process_commitment: Tuple[int, bytes],
+                          tally_commitment: Tuple[int, bytes], process_subtree_depth: int, tally_subtree_depth: int,
+                          voting_period_end: int, coordinator_pk: Tuple[bytes, bytes], new_commitment: bytes):
+    """provider.rs:141-215 without the verify key: ("process" | "tally", public inputs as
+    integers, (proof_index + 1, new_commitment)) or None.  u32 arithmetic as in the reference."""
+    message_batch_size = interactions.arity ** process_subtree_depth                       # :150
+    current_batch_index = interactions.count
+    if current_batch_index > 0:                                                             # :152-157
+        r = interactions.count % message_batch_size
+        current_batch_index -= message_batch_size if r == 0 else r
+    proof_index = process_commitment[0]
+    index_offset = proof_index * message_batch_size
+    if index_offset <= current_batch_index:                                                 # :162
+        coord_hash = poseidon_permute_hash([int.from_bytes(coordinator_pk[0], "big") % P,
+                                            int.from_bytes(coordinator_pk[1], "big") % P])  # :166-172
+        if interactions.root is None:
+            return None
+        current_batch_index -= index_offset
+        end_batch_index = min(current_batch_index + message_batch_size, interactions.count)
+        inputs = [registrations.count + 1, voting_period_end, int.from_bytes(interactions.root, "big") % P,
+                  registrations.depth, end_batch_index, current_batch_index, coord_hash,
+                  int.from_bytes(process_commitment[1], "big") % P, int.from_bytes(new_commitment, "big") % P]
+        return "process", inputs, (proof_index + 1, new_commitment)
+    proof_index = tally_commitment[0]                                                       # :196-213
+    batch_size = registrations.arity ** tally_subtree_depth
+    current_batch_index = proof_index * batch_size
+    if current_batch_index >= registrations.count + 1:
+        return None
+    inputs = [int.from_bytes(process_commitment[1], "big") % P, int.from_bytes(tally_commitment[1], "big") % P,
+              int.from_bytes(new_commitment, "big") % P, current_batch_index, registrations.count + 1]
+    return "tally", inputs, (proof_index + 1, new_commitment)
+
+
 # -- leaf hashing (provider.rs:218-287), the "next" row ------------------------
 def registration_leaf(pk_x: bytes, pk_y: bytes, timestamp: int) -> bytes:
     """hash4(pk.x, pk.y, 1, timestamp)  (provider.rs:224-233)."""

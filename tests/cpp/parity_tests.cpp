@@ -274,6 +274,18 @@ static void poll_register_interact_merge() {
     CHECK(!poll.merge_interactions().has_value());
     CHECK(poll.interactions.root == std::optional<HashBytes>(HB(G_INTERACTIONS_ROOT)));
     CHECK(poll.commitment.expected_process == G_EXPECTED_PROCESS && poll.commitment.expected_tally == G_EXPECTED_TALLY);
+    // the nine public inputs of the first process-messages proof (extrinsics.rs:621-633)
+    poll.created_at = G_CREATED_AT; poll.signup_period = G_SIGNUP_PERIOD; poll.voting_period = G_VOTING_PERIOD;
+    PublicKey coordinator{HB(G_COORDINATOR_PK[0]), HB(G_COORDINATOR_PK[1])};
+    auto pi = poll.prepare_public_inputs(coordinator, HB(G_EXPECTED_PUBLIC_INPUTS[8]));
+    CHECK(pi.has_value() && pi->process && pi->inputs.size() == 9);
+    if (pi && pi->inputs.size() == 9)
+        for (int i = 0; i < 9; i++) CHECK(pi->inputs[i].be == HB(G_EXPECTED_PUBLIC_INPUTS[i]));
+    CHECK(pi && pi->commitment.process == std::make_pair(1u, HB(G_EXPECTED_PUBLIC_INPUTS[8])));
+    if (pi) poll.commitment = pi->commitment;
+    auto ti = poll.prepare_public_inputs(coordinator, HashBytes{});
+    CHECK(ti.has_value() && !ti->process && ti->inputs.size() == 5 && ti->inputs[0].be == HB(G_EXPECTED_PUBLIC_INPUTS[8]) &&
+          ti->inputs[4].be == be32(4) && ti->commitment.tally.first == 1);
 }
 
 // ---- verify_outcome against the reference's scenario fixtures (data.rs:241-275) ---------------------

@@ -160,7 +160,11 @@ def main():
         "registrations_depth": int(re.search(r"registrations\.depth,\s*(\d+)", body).group(1)),
         "interactions_root": a[0], "process_commitment": a[1],
         "interactions_root_decimal": dec[0],
-        "coord_pub_key_hash_decimal": re.search(r'coord_pub_key_hash,\s*"(\d+)"', body).group(1)}
+        "coord_pub_key_hash_decimal": re.search(r'coord_pub_key_hash,\s*"(\d+)"', body).group(1),
+        # the nine public inputs of the first process-messages proof, as listed in the test's comment
+        # (extrinsics.rs:621-633): what prepare_public_inputs (provider.rs:141-215) must produce
+        "expected_public_inputs_decimal": re.findall(r'//\s+"(\d+)"', body),
+        "created_at_block": 1}
 
     with open(OUT, "w") as f:
         json.dump(v, f, indent=1, sort_keys=True)

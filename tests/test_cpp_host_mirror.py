@@ -56,6 +56,10 @@ def _write_golden_header(path):
         g["merge_interaction_state_success"]["expected_process"], g["merge_interaction_state_success"]["expected_tally"],
         g["process_messages_public_signals"]["registrations_depth"]))
     L.append('static const char* G_COORD_PUB_KEY_HASH_DECIMAL = "%s";' % g["process_messages_public_signals"]["coord_pub_key_hash_decimal"])
+    pm = g["process_messages_public_signals"]
+    L.append(_arr2("G_EXPECTED_PUBLIC_INPUTS", ["%064x" % int(x) for x in pm["expected_public_inputs_decimal"]]))
+    L.append("static const uint64_t G_CREATED_AT = %d, G_SIGNUP_PERIOD = %d, G_VOTING_PERIOD = %d;" % (
+        pm["created_at_block"], cfg["signup_period"], cfg["voting_period"]))
     sc = [g["scenario_1_outcome"], g["scenario_2_outcome"]]
     L.append("static const uint32_t G_OUTCOME_TALLY_RESULTS[2][25] = {%s};" % ", ".join(
         "{%s}" % ", ".join(str(x) for x in o["tally_results"]) for o in sc))

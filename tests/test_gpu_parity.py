@@ -159,6 +159,24 @@ def test_process_messages_public_signals(ib, golden):
     pk = golden["coordinator_pk"]
     hsh = ib.Poseidon.new_circom(2).hash([int(pk["x"], 16), int(pk["y"], 16)])
     assert str(hsh) == g["coord_pub_key_hash_decimal"]
+    # the whole sequence of the reference test through the Poll mirror, ending in the nine
+    # public inputs listed at extrinsics.rs:621-633 (prepare_public_inputs, provider.rs:141-215)
+    cfg = golden["poll_config"]
+    poll = ib.Poll(ib.PollConfig(cfg["registration_depth"], cfg["interaction_depth"], cfg["process_subtree_depth"],
+                                 cfg["tally_subtree_depth"], cfg["signup_period"], cfg["voting_period"]),
+                   created_at=g["created_at_block"])
+    for p in golden["participants"]:
+        poll.register_participant((H(p["x"]), H(p["y"])), golden["merge_registration_state_success"]["registration_block"])
+    poll.merge_registrations()
+    msg = golden["participant"]
+    poll.consume_interaction((H(msg["shared_pk"]["x"]), H(msg["shared_pk"]["y"])), [H(x) for x in msg["message"]])
+    poll.merge_interactions()
+    exp = [int(x) for x in g["expected_public_inputs_decimal"]]
+    kind, inputs, nxt = poll.prepare_public_inputs((H(pk["x"]), H(pk["y"])), be(exp[8]))
+    assert kind == "process" and inputs == exp and nxt.process == (1, be(exp[8]))
+    poll.commitment = nxt
+    kind, inputs, nxt = poll.prepare_public_inputs((H(pk["x"]), H(pk["y"])), bytes(32))
+    assert kind == "tally" and inputs == [exp[8], 0, 0, 0, 4] and nxt.tally[0] == 1
 
 
 def test_participant_limit_reached_quirk(ib):

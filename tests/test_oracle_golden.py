@@ -137,6 +137,22 @@ def test_process_messages_public_signals(golden):
     pk = golden["coordinator_pk"]
     hsh = O.Poseidon.new_circom(2).hash([int(pk["x"], 16) % O.P, int(pk["y"], 16) % O.P])
     assert str(hsh) == g["coord_pub_key_hash_decimal"]
+    # the nine public inputs listed at extrinsics.rs:621-633 (prepare_public_inputs, provider.rs:141-215)
+    msg = golden["participant"]
+    it = O.new_interaction_tree(golden["poll_config"]["interaction_depth"])
+    it.insert(O.interaction_leaf(H(msg["shared_pk"]["x"]), H(msg["shared_pk"]["y"]), [H(x) for x in msg["message"]]))
+    cfg = golden["poll_config"]
+    it, _, _ = O.merge_interactions(it, reg.count, cfg["process_subtree_depth"], cfg["tally_subtree_depth"])
+    exp = [int(x) for x in g["expected_public_inputs_decimal"]]
+    end = g["created_at_block"] + cfg["signup_period"] + cfg["voting_period"]                 # provider.rs:355-358
+    kind, inputs, nxt = O.prepare_public_inputs(reg, it, (0, commitment), (0, bytes(32)), cfg["process_subtree_depth"],
+                                                cfg["tally_subtree_depth"], end, (H(pk["x"]), H(pk["y"])),
+                                                exp[8].to_bytes(32, "big"))
+    assert kind == "process" and inputs == exp and nxt[0] == 1
+    # after the only process proof the tally branch is taken (index_offset 5 > batch index 0)
+    kind, inputs, nxt = O.prepare_public_inputs(reg, it, nxt, (0, bytes(32)), cfg["process_subtree_depth"],
+                                                cfg["tally_subtree_depth"], end, (H(pk["x"]), H(pk["y"])), bytes(32))
+    assert kind == "tally" and inputs == [exp[8], 0, 0, 0, 4]
 
 
 def test_participant_limit_reached_quirk():
