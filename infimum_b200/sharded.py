@@ -53,9 +53,16 @@ class ShardPlan:
 
 
 def make_plan(arity: int, full_depth: int, n_leaves: int, prepend_blank_leaf: bool, to_depth: bool,
-              world: int, min_subtrees_per_rank: int = 4) -> ShardPlan:
+              world: int, min_subtrees_per_rank: int = 64) -> ShardPlan:
     """Pick the shard level and the contiguous, count-balanced runs of
-    NON-EMPTY subtrees (all-zero subtrees are never hashed)."""
+    NON-EMPTY subtrees (all-zero subtrees are never hashed).
+
+    Ranks get whole subtrees, so their loads differ by up to one subtree: with
+    at least 64 per rank that is <= 1.6 %.  (With 4 per rank a 2^26-leaf quinary
+    tree on 8 ranks was cut into 35 subtrees, 4 or 5 per rank: 16 % imbalance,
+    34.6 ms instead of 29.9.)  A finer cut costs nothing: the number of levels
+    is the same, only more of the small top levels run after the gather, and
+    the gather grows to a few tens of KB."""
     shift = 1 if prepend_blank_leaf else 0
     n_total = n_leaves + shift
     cap = arity ** full_depth

@@ -88,7 +88,7 @@ def test_plan_balances_non_empty_subtrees():
     # 2^20 registrations + blank leaf, 8 ranks: every rank gets work
     plan = sharded.make_plan(2, 21, 1 << 20, True, False, 8)
     sizes = [e - b for b, e in plan.subtree_ranges]
-    assert min(sizes) >= 4 and max(sizes) - min(sizes) <= 1
+    assert min(sizes) >= 64 and max(sizes) - min(sizes) <= 1
     assert plan.root_depth == 21 and plan.insert_depth == 20
     covered = 0
     for r in range(8):
@@ -100,6 +100,8 @@ def test_plan_balances_non_empty_subtrees():
     plan = sharded.make_plan(5, 12, 1 << 26, False, True, 8)
     sizes = [e - b for b, e in plan.subtree_ranges]
     assert sum(sizes) == plan.n_subtrees == -(-(1 << 26) // 5 ** plan.level)
-    assert min(sizes) >= 4 and max(sizes) - min(sizes) <= 1
+    assert min(sizes) >= 64 and max(sizes) - min(sizes) <= 1
+    loads = [hi - lo for lo, hi in (plan.leaf_range(r) for r in range(8))]
+    assert max(loads) <= 1.02 * (sum(loads) / 8)              # ranks get whole subtrees: within 2 % of each other
     with pytest.raises(Exception):
         sharded.make_plan(2, 3, 9, False, True, 2)
