@@ -61,6 +61,17 @@ uint64_t pow_sat(uint64_t a, uint32_t e) {
     return (uint64_t)r;
 }
 
+// The calls below hop between devices; leave the caller's current device as it was.
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    }
+    ~DeviceRestore() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 }  // namespace
 
 struct inf_multi {
@@ -110,6 +121,7 @@ int inf_multi_init(const int* devices, int n_devices, uint32_t flags, inf_multi*
 
 void inf_multi_destroy(inf_multi* m) {
     if (!m) return;
+    DeviceRestore restore;
     for (size_t i = 0; i < m->comms.size(); i++)
         if (m->comms[i]) g_nccl.CommDestroy(m->comms[i]);
     for (size_t i = 0; i < m->ctx.size(); i++) {
@@ -131,6 +143,7 @@ int inf_multi_tree_merge(inf_multi* m, uint32_t arity, uint32_t full_depth, int 
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (full_depth > 32) return INF_ERR_BAD_DEPTH;
     const int G = (int)m->devices.size();
+    DeviceRestore restore;
     const uint64_t shift = prepend_blank_leaf ? 1 : 0, n_total = n_leaves + shift;
     const uint64_t cap = pow_sat(arity, full_depth);
     if (insert_depth) *insert_depth = 0;
@@ -278,10 +291,15 @@ int inf_multi_poseidon_hash_batch(inf_multi* m, uint32_t n_inputs, uint32_t flag
                                          j->hi - j->lo, j->out + j->lo * 32);
         return nullptr;
     };
+    DeviceRestore restore;
     std::vector<pthread_t> th(G);
-    for (int g = 1; g < G; g++) pthread_create(&th[g], nullptr, run, &jobs[g]);
+    std::vector<bool> started(G, false);
+    for (int g = 1; g < G; g++) started[g] = pthread_create(&th[g], nullptr, run, &jobs[g]) == 0;
     run(&jobs[0]);
-    for (int g = 1; g < G; g++) pthread_join(th[g], nullptr);
+    for (int g = 1; g < G; g++) {
+        if (started[g]) pthread_join(th[g], nullptr);
+        else run(&jobs[g]);                      // no thread to be had: do the slice here
+    }
     for (int g = 0; g < G; g++)
         if (rcs[g]) return rcs[g];
     return INF_OK;

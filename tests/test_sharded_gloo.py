@@ -105,3 +105,43 @@ def test_plan_balances_non_empty_subtrees():
     assert max(loads) <= 1.02 * (sum(loads) / 8)              # ranks get whole subtrees: within 2 % of each other
     with pytest.raises(Exception):
         sharded.make_plan(2, 3, 9, False, True, 2)
+
+
+def test_plan_properties_random_shapes():
+    """The plan, for random tree shapes and world sizes, with the default
+    granularity: subtree runs are contiguous and cover every subtree, leaf
+    ranges partition the leaves, the blank leaf lives on the first rank that
+    has work, and the emulated sharded merge (every rank of the plan back to
+    back, oracle data plane) reproduces insert x N + merge."""
+    import random
+    from infimum_b200 import sharded
+    rng = random.Random(20261018)
+    backend = OracleBackend()
+    for case in range(60):
+        arity = rng.choice((2, 5))
+        full_depth = rng.randint(1, 11) if arity == 2 else rng.randint(1, 4)
+        blank = rng.random() < 0.5
+        cap = arity ** full_depth - (1 if blank else 0)
+        n = rng.choice((0, 1, cap, rng.randint(0, cap), rng.randint(0, min(cap, 40))))
+        to_depth = rng.random() < 0.5
+        world = rng.choice((1, 2, 3, 8))
+        plan = sharded.make_plan(arity, full_depth, n, blank, to_depth, world,
+                                 min_subtrees_per_rank=rng.choice((1, 2, 4, 64)))
+        assert plan.subtree_ranges[0][0] == 0 and plan.subtree_ranges[-1][1] == plan.n_subtrees
+        assert all(plan.subtree_ranges[r][1] == plan.subtree_ranges[r + 1][0] for r in range(world - 1))
+        covered = 0
+        for r in range(world):
+            lo, hi = plan.leaf_range(r)
+            assert lo == covered and hi >= lo
+            covered = hi
+        assert covered == n
+        assert sum(plan.rank_shift(r) for r in range(world)) == (1 if blank and plan.n_total else 0)
+        leaves = random_fr_bytes(max(n, 1), seed=case)[:n]
+        root = sharded.emulated_sharded_merge(torch.from_numpy(leaves.copy()), plan, backend)
+        rc, exp, depth, count = c_oracle.tree_insert_merge(arity, full_depth, blank, to_depth, leaves)
+        assert rc in (0, 2)
+        if plan.n_total == 0:
+            assert root is None
+        else:
+            assert root.numpy().tobytes() == exp, (arity, full_depth, n, blank, to_depth, world)
+            assert plan.insert_depth == depth
