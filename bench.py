@@ -510,6 +510,26 @@ def run_ours(args, rank, world, local_rank):
         "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "bytes_per_hash": 96},
     }
+    # executed work: multiply-pipe instructions of ONE hash2 counted in the SASS of the shipped kernel
+    # (tools/sass_count.py: IMAD.WIDE(.X) and IMAD.HI occupy the pipe 4 cycles per warp, IMAD 2), against the
+    # pipe's capacity of one warp-cycle per sub-partition per clock
+    executed = {"imad_wide": 56793, "imad_hi": 3056, "imad": 3056, "source": "static (tools/sass_count.py, round 1)"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_count
+        live = sass_count.count(os.path.join(ROOT, "infimum_b200", "_build", "poseidon_t3.o"), "hash_batch_kernelILb0",
+                                [4, 28, 3])
+        executed = {"imad_wide": live["wide"], "imad_hi": live["hi"], "imad": live["imad"],
+                    "all_instructions": sum(live.values()), "source": "cuobjdump -sass of the shipped poseidon_t3.o"}
+    except Exception:
+        pass
+    pipe_cycles = 4 * (executed["imad_wide"] + executed["imad_hi"]) + 2 * executed["imad"]
+    pipe_bound = sms * 4 * sm_max_mhz * 1e6 / pipe_cycles * 32          # hashes/s with the multiply pipe never idle
+    executed.update({"pipe_cycles_per_hash_per_warp": pipe_cycles, "pipe_bound_hashes_per_s": pipe_bound,
+                     "frac_of_pipe_bound": (n / (avg_launch_ms * 1e-3)) / pipe_bound,
+                     "wide_per_s": executed["imad_wide"] * n / (avg_launch_ms * 1e-3) / 1e12,
+                     "wide_per_s_measured_peak": (meas.get("imad_wide_carry_chain_x2") or 0) / 2 or None})
+    roofline["executed"] = executed
     base, _, _ = cpu_baseline_hash2(12.0) if world == 1 and not args.no_cpu_baseline else (None, 0, 0)
 
     line = {

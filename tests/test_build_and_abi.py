@@ -57,6 +57,21 @@ def test_sass_is_integer_pipe_code():
     assert "STL" not in sass and "LDL" not in sass
 
 
+def test_executed_multiply_count_per_hash2():
+    """Dynamic multiply-pipe instruction count of one hash2 in the shipped SASS
+    (what bench.py's roofline.executed reports): a regression guard on the
+    schedule (squarings, paired partial rounds, one canonical output row)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import sass_count
+    obj = os.path.join(root, "infimum_b200", "_build", "poseidon_t3.o")
+    for fn in ("hash_batch_kernelILb0", "17tree_level_kernel"):
+        c = sass_count.count(obj, fn, [4, 28, 3])
+        assert 50000 < c["wide"] <= 57000 and c["hi"] <= 3200 and c["imad"] <= 3200, c
+        assert sum(c.values()) <= 90000, c
+
+
 def test_product_does_not_import_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for dirpath, _, files in os.walk(os.path.join(root, "infimum_b200")):
