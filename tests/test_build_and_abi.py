@@ -57,6 +57,24 @@ def test_sass_is_integer_pipe_code():
     assert "STL" not in sass and "LDL" not in sass
 
 
+def test_header_is_plain_c(tmp_path, built):
+    """The boundary is a C ABI: the header must compile as C99 and a C program
+    must link against the library and get the no-device error, not a crash."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include "infimum_b200.h"\n'
+                   'int main(void) { inf_ctx* c = 0; int rc = inf_init(0, &c);\n'
+                   '  printf("%d %s\\n", rc, inf_strerror(rc)); if (c) inf_destroy(c); return 0; }\n')
+    exe = tmp_path / "c_abi"
+    libdir = os.path.dirname(os.path.abspath(built.LIB_PATH))
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-linfimum_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    import torch
+    assert int(out[0]) == (0 if torch.cuda.is_available() else built.ERR_NO_DEVICE)
+
+
 def test_executed_multiply_count_per_hash2():
     """Dynamic multiply-pipe instruction count of one hash2 in the shipped SASS
     (what bench.py's roofline.executed reports): a regression guard on the
