@@ -236,7 +236,7 @@ std::vector<uint32_t> build_opt(void) {
 }
 }  // namespace
 
-std::vector<uint32_t> build_opt_table(int t) {
+static std::vector<uint32_t> build_opt_uncached(int t) {
     switch (t) {
         case 2: return build_opt<2>();
         case 3: return build_opt<3>();
@@ -247,6 +247,16 @@ std::vector<uint32_t> build_opt_table(int t) {
         case 8: return build_opt<8>();
         default: return {};
     }
+}
+
+// Derived once per process (a context per device asks for the same tables).
+std::vector<uint32_t> build_opt_table(int t) {
+    static std::map<int, std::vector<uint32_t>> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(t);
+    if (it == cache.end()) it = cache.emplace(t, build_opt_uncached(t)).first;
+    return it->second;
 }
 
 std::vector<uint32_t> build_dense_table(int t) {
