@@ -346,10 +346,6 @@ static int occupancy_pad() {
     return pad;
 }
 
-cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t words) {
-    if (words != (size_t)Layout<T>::WORDS) return cudaErrorInvalidValue;
-    return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
-}
 
 cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, uint64_t n,
                                                 const TagArg& tag, bool le, cudaStream_t st) {
@@ -381,6 +377,16 @@ static uint64_t coop_max() {
         set_on[dev] = true;
     }
     return (uint64_t)v;
+}
+
+// Called by inf_init for every width on the context's device, under the init
+// lock: also the place where the per-device function attributes (and the
+// statics above) are settled, before any concurrent launches can happen.
+cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t words) {
+    if (words != (size_t)Layout<T>::WORDS) return cudaErrorInvalidValue;
+    occupancy_pad();
+    coop_max();
+    return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
 }
 
 cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift, uint64_t n_in,
