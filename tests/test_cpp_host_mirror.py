@@ -25,7 +25,7 @@ def _arr2(name, rows):
 def _write_golden_header(path):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
     L = ["// generated from tests/golden/reference_vectors.json by tests/test_cpp_host_mirror.py", "#pragma once",
-         "#include <cstdint>"]
+         "#include <stdint.h>"]
     L.append(_arr("G_FR_ONE_EXPECTED_BE", g["fr_one"]["expected_be"]))
     L.append(_arr("G_BYTES_ONES_TWOS_BE", g["bytes_ones_twos"]["expected_be"]))
     L.append(_arr("G_BYTES_ONES_TWOS_LE", g["bytes_ones_twos"]["expected_le"]))
@@ -88,6 +88,34 @@ def build():
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return BIN
+
+
+def build_cpu():
+    """The same test source linked against tests/cpp/fake_infimum.c (the oracle behind the C ABI's
+    signatures; test infrastructure) ahead of the real library: runs without a GPU."""
+    build()
+    out = os.path.join(CPP, "_build")
+    exe = os.path.join(out, "parity_tests_cpu")
+    inc = ["-I", out, "-I", os.path.join(ROOT, "include")]
+    r = subprocess.run(["gcc", "-O2", "-std=c11", "-Wno-unused-variable", "-Wno-unused-const-variable"] + inc +
+                       ["-c", os.path.join(CPP, "fake_infimum.c"), "-o", os.path.join(out, "fake_infimum.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cmd = ["g++", "-O1", "-std=c++17"] + inc + [os.path.join(CPP, "parity_tests.cpp"), os.path.join(out, "fake_infimum.o"),
+           "-o", exe, "-L", os.path.join(ROOT, "infimum_b200"), "-linfimum_b200", "-L", os.path.join(ROOT, "oracle"),
+           "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "infimum_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
+           "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_parity_tests_pass_on_cpu_over_the_fake_library():
+    exe = build_cpu()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "0 failed" in r.stdout
 
 
 def test_cpp_host_mirror_compiles_and_links():
