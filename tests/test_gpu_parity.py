@@ -226,8 +226,9 @@ def test_optimised_kernel_equals_dense_kernel_on_device(ib, n_inputs):
     assert (h.hash_batch(raw) == h.hash_batch(raw, dense=True)).all()
 
 
-def test_hash2_2_20_pairs_bit_exact_vs_oracle(ib):
-    """BASELINE config 2 at an oracle-affordable size: every output compared."""
+def test_hash2_2_17_pairs_bit_exact_vs_oracle(ib):
+    """A quick 2^17-pair batch, every output compared (the full 2^24 pairs of
+    BASELINE config 2 are in tests/test_gpu_fullsize.py)."""
     n = 1 << 17
     raw = random_fr_bytes(2 * n)
     got = ib.Poseidon.new_circom(2).hash_batch(raw)
