@@ -30,7 +30,7 @@ NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wno
                      "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 CU_SOURCES = ["poseidon_t%d.cu" % t for t in range(2, 9)] + ["dense_generic.cu", "leaves.cu", "tree_paths.cu", "imad_peak.cu", "multi.cu", "capi.cu"]
 CXX_SOURCES = ["host_params.cpp"]
-HEADERS = ["fr.cuh", "poseidon.cuh", "poseidon_tu.cuh", "launch.h", "host_fr.h", "host_params.h",
+HEADERS = ["fr.cuh", "poseidon.cuh", "coop.cuh", "poseidon_tu.cuh", "launch.h", "host_fr.h", "host_params.h",
            os.path.join(ROOT, "include", "infimum_b200.h")]
 
 
@@ -80,7 +80,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
     stamp = HOSTEMU + ".sha"
     if force or not os.path.exists(HOSTEMU) or not os.path.exists(stamp) or open(stamp).read() != dig:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", CSRC,
-               "-o", HOSTEMU] + he_src
+               "-o", HOSTEMU] + he_src + ["-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("hostemu build failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -194,36 +194,65 @@ std::vector<uint32_t> build_opt(void) {
     }
     const Mat& PRE = N;
 
+    // unit leading coefficient (Layout<T> in poseidon.cuh, derive() in tests/opt_model.py):
+    // lambda_0 = 1, lambda_{j+1} = m00_j lambda_j^5; v' = v / lambda_{j+1}, k' = k / lambda_{j+1},
+    // w' = w lambda_j^5
+    auto kv = [&](int j) -> const F& { return j + 1 < rp ? k[j + 1] : D[0]; };   // constant folded into round j's row
+    auto pow5 = [](const F& x) { F x2 = mul(x, x); return mul(mul(x2, x2), x); };
+    std::vector<std::vector<F>> vs(rp), ws(rp);
+    std::vector<F> ks(rp);
+    F lam = one();
+    for (int j = 0; j < rp; j++) {
+        const F l5 = pow5(lam);
+        const F nxt = mul(row0[j][0], l5);
+        if (nxt.is_zero()) throw std::runtime_error("zero pivot in the partial-round scaling");
+        const F inv_n = inv(nxt);
+        vs[j].resize(T - 1);
+        ws[j].resize(T - 1);
+        for (int i = 0; i < T - 1; i++) {
+            vs[j][i] = mul(row0[j][i + 1], inv_n);
+            ws[j][i] = mul(wcol[j][i], l5);
+        }
+        ks[j] = mul(kv(j), inv_n);
+        lam = nxt;
+    }
+    const F lam5 = pow5(lam);
+
     put_canon(tbl, L::R2, R2);
     for (int i = 0; i < T; i++) put_v(tbl, L::IN_V + i, C(0, i));
     put_mont(tbl, L::S0, C(0, 0));
     for (int i = 0; i < T * T; i++) {
         put_mont(tbl, L::FULL_M + i, M[i]);
         put_mont(tbl, L::PRE_M + i, PRE[i]);
+        put_mont(tbl, L::TAIL0_M + i, i % T == 0 ? mul(M[i], lam5) : M[i]);
     }
     for (int r = 0; r < 3; r++)
         for (int i = 0; i < T; i++) put_v(tbl, L::FULL_V + r * T + i, C(r + 1, i));
     put_v(tbl, L::PRE_V + 0, k[0]);     // remaining PRE_V entries stay zero
-    auto kv = [&](int j) -> const F& { return j + 1 < rp ? k[j + 1] : D[0]; };   // constant folded into round j's row
     for (int jp = 0; jp < L::N_PAIRS; jp++) {
         const int a = 2 * jp, b = 2 * jp + 1, base = L::PART + jp * L::PAIR_STRIDE;
-        for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[a][i]);
-        put_v(tbl, base + T, kv(a));
-        for (int i = 0; i < T; i++) put_mont(tbl, base + T + 1 + i, row0[b][i]);
-        F c = zero();                                          // c_B = row0_B[1..] . w_A
-        for (int i = 0; i < T - 1; i++) c = add(c, mul(row0[b][i + 1], wcol[a][i]));
-        put_mont(tbl, base + 2 * T + 1, c);
-        put_v(tbl, base + 2 * T + 2, kv(b));
+        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + L::P_VA + i, vs[a][i]);
+        put_v(tbl, base + L::P_KA, ks[a]);
+        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + L::P_VB + i, vs[b][i]);
+        F c = zero();                                          // c_B = v'_B . w'_A
+        for (int i = 0; i < T - 1; i++) c = add(c, mul(vs[b][i], ws[a][i]));
+        put_mont(tbl, base + L::P_CB, c);
+        put_v(tbl, base + L::P_KB, ks[b]);
         for (int i = 0; i < T - 1; i++) {
-            put_mont(tbl, base + 2 * T + 3 + 2 * i, wcol[a][i]);
-            put_mont(tbl, base + 2 * T + 4 + 2 * i, wcol[b][i]);
+            put_mont(tbl, base + L::P_W + 2 * i, ws[a][i]);
+            put_mont(tbl, base + L::P_W + 2 * i + 1, ws[b][i]);
         }
     }
     for (int js = 0; js < L::N_SINGLES; js++) {
         const int j = 2 * L::N_PAIRS + js, base = L::SINGLES + js * L::SINGLE_STRIDE;
-        for (int i = 0; i < T; i++) put_mont(tbl, base + i, row0[j][i]);
-        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + T + i, wcol[j][i]);
-        put_v(tbl, base + 2 * T - 1, kv(j));
+        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + L::S_V + i, vs[j][i]);
+        for (int i = 0; i < T - 1; i++) put_mont(tbl, base + L::S_W + i, ws[j][i]);
+        put_v(tbl, base + L::S_K, ks[j]);
+    }
+    for (int j = 1; j < rp; j++) {
+        F c = zero();
+        for (int i = 0; i < T - 1; i++) c = add(c, mul(vs[j][i], ws[j - 1][i]));
+        put_mont(tbl, L::COOP_C + j, c);
     }
     for (int i = 1; i < T; i++) put_mont(tbl, L::LAST_D + i - 1, D[i]);
     for (int r = 0; r < 3; r++)

@@ -3,8 +3,14 @@
 // CPU test-suite can exercise the exact kernel logic where there is no GPU.
 // TEST SUPPORT: built as libinfimum_hostemu.so, never loaded by the product.
 #define INF_HOST_CHECKS 1
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
+#include "coop.cuh"
 #include "host_params.h"
 #include "poseidon.cuh"
 
@@ -20,7 +26,123 @@ static void hash_t(const uint8_t* in, const uint8_t* tag, uint8_t* out, int le, 
     memcpy(out, ow, 32);
 }
 
+// ---- the warp-cooperative schedule (coop.cuh) with one host thread per role -------------
+// Barriers follow the PTX named-barrier rules the device Bus relies on: a generation
+// completes when the expected number of roles has entered (arrive = enter without
+// waiting, wait = enter and block); a role entering the same barrier twice in one
+// generation is a protocol error and is counted.
+namespace {
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0;
+    unsigned entered = 0;            // bit per role, this generation
+    unsigned long long gen = 0;
+    std::atomic<int>* errors = nullptr;
+    void enter(int role, int expected, bool block) {
+        std::unique_lock<std::mutex> lk(m);
+        if (entered & (1u << role)) ++*errors;
+        entered |= 1u << role;
+        if (++count == expected) {
+            count = 0;
+            entered = 0;
+            gen++;
+            cv.notify_all();
+        } else if (block) {
+            const unsigned long long g = gen;
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+};
+
+template <int T>
+struct HostBus {
+    typedef uint32_t* Slot;
+    uint32_t xs[2][T][8], zs[3][8], vs[2][8], ps[3][T][8];
+    HostBarrier blk, zb[3], vb[2], pb[3], pro;
+    std::atomic<int> errors{0};
+    unsigned jitter = 0;             // roles (bit mask) that dawdle before every barrier
+    HostBus() {
+        for (HostBarrier* b : {&blk, &zb[0], &zb[1], &zb[2], &vb[0], &vb[1], &pb[0], &pb[1], &pb[2], &pro}) b->errors = &errors;
+    }
+    struct View {                    // what one role's thread sees
+        HostBus& b;
+        int role;
+        Slot x(int buf, int i) const { return b.xs[buf][i]; }
+        Slot z(int par) const { return b.zs[par]; }
+        Slot v(int par) const { return b.vs[par]; }
+        Slot p(int par, int i) const { return b.ps[par][i]; }
+        void put(Slot d, const uint32_t (&val)[8]) const { memcpy(d, val, 32); }
+        void get(uint32_t (&val)[8], Slot s) const { memcpy(val, s, 32); }
+        void dawdle() const {
+            if (b.jitter & (1u << role)) std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+        void block() const { dawdle(); b.blk.enter(role, T + 1, true); }
+        void z_arrive(int par) const { dawdle(); b.zb[par].enter(role, T + 1, false); }
+        void z_wait(int par) const { dawdle(); b.zb[par].enter(role, T + 1, true); }
+        void v_arrive(int par) const { dawdle(); b.vb[par].enter(role, 2, false); }
+        void v_wait(int par) const { dawdle(); b.vb[par].enter(role, 2, true); }
+        void p_arrive(int par) const { dawdle(); b.pb[par].enter(role, T, false); }
+        void p_wait(int par) const { dawdle(); b.pb[par].enter(role, T, true); }
+        void pro_arrive() const { dawdle(); b.pro.enter(role, T, false); }
+        void pro_wait() const { dawdle(); b.pro.enter(role, T, true); }
+    };
+};
+
+template <int T>
+int coop_hash_t(const uint8_t* in, uint8_t* out, unsigned jitter, const uint32_t* tbl) {
+    using L = Layout<T>;
+    HostBus<T> bus;
+    bus.jitter = jitter;
+    uint32_t result[8] = {};
+    std::thread th[T + 1];
+    for (int role = 0; role <= T; role++)
+        th[role] = std::thread([&, role] {
+            uint32_t s[8] = {}, h[8];
+            if (role == 0) {
+                memcpy(s, tbl + L::S0 * 8, 32);
+            } else if (role < T) {
+                uint32_t wd[8], raw[8];
+                memcpy(wd, in + 32 * (role - 1), 32);
+                words_to_limbs<false>(raw, wd);
+                absorb<T>(s, raw, role, tbl);
+            }
+            typename HostBus<T>::View view{bus, role};
+            coop_hash<T>(h, s, role, view, tbl);
+            if (role == 0) memcpy(result, h, 32);
+        });
+    for (auto& t : th) t.join();
+    uint32_t ow[8];
+    limbs_to_words<false>(ow, result);
+    memcpy(out, ow, 32);
+    return bus.errors.load();
+}
+}  // namespace
+
 extern "C" {
+
+// One hash through the warp-cooperative schedule, one thread per role.  Returns the
+// number of barrier-protocol errors (0 expected), or -1 for an unsupported width.
+int hostemu_coop_hash(int t, const uint8_t* in, uint8_t* out, unsigned jitter) {
+    static std::vector<uint32_t> tables[14];
+    static std::mutex mu;
+    if (t < 2 || t > 8) return -1;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (tables[t].empty()) tables[t] = host::build_opt_table(t);
+    }
+    const uint32_t* tbl = tables[t].data();
+    switch (t) {
+        case 2: return coop_hash_t<2>(in, out, jitter, tbl);
+        case 3: return coop_hash_t<3>(in, out, jitter, tbl);
+        case 4: return coop_hash_t<4>(in, out, jitter, tbl);
+        case 5: return coop_hash_t<5>(in, out, jitter, tbl);
+        case 6: return coop_hash_t<6>(in, out, jitter, tbl);
+        case 7: return coop_hash_t<7>(in, out, jitter, tbl);
+        case 8: return coop_hash_t<8>(in, out, jitter, tbl);
+    }
+    return -1;
+}
 
 unsigned long long hostemu_overflow_count() { return host_overflow_count; }
 

@@ -31,9 +31,10 @@ INF_HD constexpr int partial_rounds(int t) {
 
 // Paired partial rounds (widths >= 4 with an even number of partial rounds):
 // two partial rounds share the update of s[1..]:
-//     round A:  x_a = s0^5 ;  n  = row0_A . (x_a, s[1..]) + k_A
-//     round B:  x_b = n^5  ;  s0 = row0_B . (x_b, s[1..]) + c_B * x_a + k_B ,   c_B = row0_B[1..] . w_A
-//     then      s_i += w_A[i] * x_a + w_B[i] * x_b          (one 2-term lazy dot, ONE reduction)
+//     round A:  z_a = u^5 ;  n = z_a + v'_A . s[1..] + k'_A
+//     round B:  z_b = n^5 ;  u = z_b + v'_B . s[1..] + c_B * z_a + k'_B ,   c_B = v'_B . w'_A
+//     then      s_i += w'_A[i] * z_a + w'_B[i] * z_b        (one 2-term lazy dot, ONE reduction)
+// (u, v', w', k': the unit-leading-coefficient form described at Layout)
 // which is the same arithmetic (s_i after round A is s_i + w_A[i] x_a, substituted
 // into round B's row) with T-1 fewer reductions and one more product per pair:
 // -4.6 % (t=3) .. -10 % (t=6) multiply-pipe instructions per round.  An odd number
@@ -51,6 +52,15 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 // Montgomery form (x*R mod p) except the "V" entries, which are x*R^2 mod p
 // (they enter an accumulator that is then divided by R), and OUT_ROW, which is
 // canonical.
+//
+// Partial rounds carry s0 as u = s0 / lambda_j (lambda_0 = 1, lambda_{j+1} =
+// m00_j lambda_j^5), which makes the coefficient of the fresh S-box output one:
+//     z = u^5 ;  u' = z + v'_j . s[1..] + k'_j ;  s_i' = s_i + w'_j[i] z
+// (v' = v / lambda_{j+1}, k' = k / lambda_{j+1}, w' = w lambda_j^5; exact field
+// identities, tests/opt_model.py).  One product less per partial round than the
+// plain sparse form, and nothing but an addition between one S-box and the next.
+// The scale comes off in the first round of the second half, whose matrix has
+// column 0 multiplied by lambda_RP^5 (TAIL0_M).
 template <int T>
 struct Layout {
     static constexpr int RP = partial_rounds(T);
@@ -59,15 +69,16 @@ struct Layout {
     static constexpr int S0 = IN_V + T;                  // C_0[0] * R   (state[0] when tag == 0)
     static constexpr int FULL_M = S0 + 1;                // [T][T] MDS
     static constexpr int PRE_M = FULL_M + T * T;         // [T][T] MDS with the sparse prefix merged
-    static constexpr int FULL_V = PRE_M + T * T;         // [3][T] C_{r+1}, r = 0..2
+    static constexpr int TAIL0_M = PRE_M + T * T;        // [T][T] MDS, column 0 times lambda_RP^5
+    static constexpr int FULL_V = TAIL0_M + T * T;       // [3][T] C_{r+1}, r = 0..2
     static constexpr int PRE_V = FULL_V + 3 * T;         // [T]   (k_0, 0, ..., 0)
     static constexpr bool PAIRED = paired_rounds(T);
-    // single round record [2T]   : row0[T], w[T-1], kv
-    // pair record        [4T+1] : row0_A[T], kv_A, row0_B[T], c_B, kv_B, (w_A[i], w_B[i]) for i = 1..T-1
+    // single round record [2T-1] : v'[T-1], w'[T-1], k'
+    // pair record        [4T-1] : v'_A[T-1], k'_A, v'_B[T-1], c_B, k'_B, (w'_A[i], w'_B[i]) for i = 1..T-1
     // PAIRED: RP/2 pair records, then one single record if RP is odd; else RP single records.
     static constexpr int PART = PRE_V + T;
-    static constexpr int PAIR_STRIDE = 4 * T + 1;
-    static constexpr int SINGLE_STRIDE = 2 * T;
+    static constexpr int PAIR_STRIDE = 4 * T - 1;
+    static constexpr int SINGLE_STRIDE = 2 * T - 1;
     static constexpr int N_PAIRS = PAIRED ? RP / 2 : 0;
     static constexpr int N_SINGLES = PAIRED ? RP % 2 : RP;
     static constexpr int SINGLES = PART + N_PAIRS * PAIR_STRIDE;
@@ -75,8 +86,15 @@ struct Layout {
     static constexpr int TAIL_V = LAST_D + (T - 1);      // [3][T] C_{4+RP+r+1}, r = 0..2
     static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
     static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
-    static constexpr int COUNT = OUT_ROW_MONT + T;
+    // c_j = v'_j . w'_{j-1} for every partial round j (c_0 = 0): lets the warp-cooperative
+    // kernel (coop.cuh) form v'_j . s[1..] from the state of one round earlier
+    static constexpr int COOP_C = OUT_ROW_MONT + T;      // [RP]
+    static constexpr int COUNT = COOP_C + RP;
     static constexpr int WORDS = COUNT * 8;
+    // offsets inside a pair record
+    static constexpr int P_VA = 0, P_KA = T - 1, P_VB = T, P_CB = 2 * T - 1, P_KB = 2 * T, P_W = 2 * T + 1;
+    // offsets inside a single record
+    static constexpr int S_V = 0, S_W = T - 1, S_K = 2 * T - 2;
 };
 
 // out = ( sum_j a[j] * b[j] + V ) / R, then (RANGE_STEP) the cheap range step.
@@ -128,60 +146,59 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     }
 
     // ---- partial rounds -----------------------------------------------------
+    // q[0..T-2] = s[1..T-1], q[T-1] = z_a, q[T] = z_b: contiguous, so that the lazy
+    // dots stride over (s[1..], z_a) and (z_a, z_b).  s[0] holds u.
+    // Rows over s[1..] get a range step of their own from width 5 on: the sum
+    // with z (< 1.66 p) must stay below 2^256 and, after its step, below 2^255.
+    constexpr bool RI = T >= 5;
+    uint32_t q[T + 1][8];
+#pragma unroll
+    for (int i = 1; i < T; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[i - 1][k] = s[i][k];
     if constexpr (L::N_PAIRS > 0) {
-        // q[0] = S-box output of the current round, q[1..T-1] = s[1..T-1],
-        // q[T] = x_a, q[T+1] = x_b (contiguous so that the lazy dots can stride over them)
-        uint32_t q[T + 2][8];
-#pragma unroll
-        for (int i = 1; i < T; i++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[i][k] = s[i][k];
 #pragma unroll 1
         for (int j = 0; j < L::N_PAIRS; j++) {
             const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
             uint32_t n[8];
-            sbox(q[0], s[0]);                                                   // round A
+            sbox(q[T - 1], s[0]);                                               // round A: z_a = u^5
+            dot<T - 1, 8, RI>(n, &q[0][0], pt + L::P_VA * 8, pt + L::P_KA * 8);
+            add8(n, n, q[T - 1]);
+            csub2p(n);
+            sbox(q[T], n);                                                      // round B: z_b = n^5
+            dot<T, 8, RI>(s[0], &q[0][0], pt + L::P_VB * 8, pt + L::P_KB * 8);  // v'_B . s[1..] + c_B z_a + k'_B
+            add8(s[0], s[0], q[T]);
+            csub2p(s[0]);
 #pragma unroll
-            for (int k = 0; k < 8; k++) q[T][k] = q[0][k];
-            dot<T, 8, RS>(n, &q[0][0], pt, pt + T * 8);
-            sbox(q[0], n);                                                      // round B
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[T + 1][k] = q[0][k];
-            dot<T + 1, 8, RS>(s[0], &q[0][0], pt + (T + 1) * 8, pt + (2 * T + 2) * 8);
-#pragma unroll
-            for (int i = 1; i < T; i++) {                                       // s_i += w_A x_a + w_B x_b
+            for (int i = 1; i < T; i++) {                                       // s_i += w'_A z_a + w'_B z_b
                 uint32_t w[8];
-                // (x_a, x_b < 1.6 p, constants < p: w < 1.61 p, no range step needed before the add)
-                dot<2, 8, false>(w, &q[T][0], pt + (2 * T + 3 + 2 * (i - 1)) * 8, nullptr);
-                add8(q[i], q[i], w);
-                csub2p(q[i]);
+                // (z_a, z_b < 1.7 p, constants < p: w < 1.65 p, no range step needed before the add)
+                dot<2, 8, false>(w, &q[T - 1][0], pt + (L::P_W + 2 * (i - 1)) * 8, nullptr);
+                add8(q[i - 1], q[i - 1], w);
+                csub2p(q[i - 1]);
             }
         }
-#pragma unroll
-        for (int i = 1; i < T; i++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) s[i][k] = q[i][k];
     }
 #pragma unroll 1
     for (int j = 0; j < L::N_SINGLES; j++) {
         const uint32_t* pt = tbl + (L::SINGLES + j * L::SINGLE_STRIDE) * 8;
-        sbox(x[0], s[0]);
-        // element 0 temporarily holds the S-box output so that the dot runs
-        // over the contiguous state
-#pragma unroll
-        for (int k = 0; k < 8; k++) s[0][k] = x[0][k];
         uint32_t n0[8];
-        dot<T, 8, RS>(n0, &s[0][0], pt, pt + (2 * T - 1) * 8);
+        sbox(q[T - 1], s[0]);
+        dot<T - 1, 8, RI>(n0, &q[0][0], pt + L::S_V * 8, pt + L::S_K * 8);
+        add8(s[0], n0, q[T - 1]);
+        csub2p(s[0]);
 #pragma unroll
         for (int i = 1; i < T; i++) {
             uint32_t w[8];
-            mont_mul(w, x[0], pt + (T + i - 1) * 8);
-            add8(s[i], s[i], w);
-            csub2p(s[i]);
+            mont_mul(w, q[T - 1], pt + (L::S_W + i - 1) * 8);
+            add8(q[i - 1], q[i - 1], w);
+            csub2p(q[i - 1]);
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) s[0][k] = n0[k];
     }
+#pragma unroll
+    for (int i = 1; i < T; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[i][k] = q[i - 1][k];
     // remaining constants of the first tail round on elements 1..T-1
 #pragma unroll
     for (int i = 1; i < T; i++) {
@@ -192,7 +209,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     // ---- second half: 3 full rounds, then the output row --------------------
 #pragma unroll 1
     for (int r = 0; r < 3; r++) {
-        const uint32_t* m = tbl + L::FULL_M * 8;
+        const uint32_t* m = tbl + (r == 0 ? L::TAIL0_M : L::FULL_M) * 8;   // s[0] still holds u: see Layout
         const uint32_t* v = tbl + (L::TAIL_V + r * T) * 8;
 #pragma unroll
         for (int i = 0; i < T; i++) sbox(x[i], s[i]);

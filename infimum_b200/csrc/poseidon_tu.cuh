@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 
+#include "coop.cuh"
 #include "launch.h"
 #include "poseidon.cuh"
 
@@ -80,63 +81,81 @@ tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-cooperative tree level, for the levels near the root.
+// Warp-cooperative tree level, for the levels near the root (schedule: coop.cuh).
 //
-// A level with fewer nodes than resident threads costs one single-thread hash
-// latency (~190 us: a lone warp needs 810 cycles per dependent multiplication,
-// profiles/r01_imad_microbench.md) whatever its size.  Here T warps share 32
-// hashes: warp w owns state element w of all 32 (lane = hash), the warps run on
-// different sub-partitions, and the state is staged through shared memory:
-//   full round     every warp: own S-box, publish it, barrier, own MDS row
-//                  (1 S-box + 1 row instead of T + T on the critical path)
-//   partial pair   warp 0 carries only the chain  S-box, x_a*m00, S-box, x_b*m00':
-//                  the products of the two rows that do not involve the fresh
-//                  S-box output (s_w*rowA[w], s_w*rowB[w], c_B*x_a) and the updates
-//                  s_w += w_A x_a + w_B x_b are formed by warps 1..T-1 meanwhile
-//                  and only added in (separately reduced, so the sums agree mod p)
-// Same tables, same field values, so results are bit-identical to the per-thread
-// kernel; per pair the critical path is 944 multiply-pipe instructions instead
-// of 1 664 (t=3) / 2 648 (t=6).
-// Shared layout [element][limb][lane]: consecutive lanes hit consecutive banks.
+// T + 1 warps share 32 hashes (lane = hash): warp roles are the roles of
+// coop.cuh, published values live in shared memory as [limb][lane] (consecutive
+// lanes hit consecutive banks), and roles wait for each other on named barriers
+// (producer bar.arrive, consumer bar.sync), so that the chain warp never waits
+// for anything but the value it needs next.  Block-wide barriers only in code
+// every warp runs through.
+constexpr int COOP_WARPS = T + 1;
+// The chain warp should have a sub-partition to itself: warps map to sub-partitions
+// by index mod 4, so with 5..7 warps that is warp 3.
+constexpr int COOP_CHAIN_WARP = (COOP_WARPS >= 5 && COOP_WARPS <= 7) ? 3 : 0;
+
 struct CoopSmem {
-    uint32_t x[2][T][8][32];      // S-box outputs of a full round, double buffered
-    // partial rounds, everything double buffered by pair parity:
-    uint32_t xa[2][8][32], xb[2][8][32];   // S-box outputs of rounds A and B (warp 0)
-    uint32_t pa[2][T][8][32];              // s_w * rowA[w] / R   (warp w >= 1)
-    uint32_t pb[2][T][8][32];              // s_w * rowB[w] / R   (warp w >= 1)
-    uint32_t cx[2][8][32];                 // c_B * x_a / R       (warp 1)
-    uint32_t s[T][8][32];                  // s[1..T-1] for the odd round out
+    uint32_t x[2][T][8][32];
+    uint32_t z[3][8][32];
+    uint32_t v[2][8][32];
+    uint32_t p[3][T][8][32];
 };
 
-__device__ __forceinline__ void sm_put(uint32_t (*dst)[32], const uint32_t (&v)[8], int lane) {
+struct CoopBus {
+    typedef uint32_t (*Slot)[32];
+    CoopSmem& sm;
+    const int lane;
+    enum { BAR_Z = 1, BAR_V = 4, BAR_P = 6, BAR_PRO = 9 };
+    __device__ __forceinline__ Slot x(int buf, int i) const { return sm.x[buf][i]; }
+    __device__ __forceinline__ Slot z(int par) const { return sm.z[par]; }
+    __device__ __forceinline__ Slot v(int par) const { return sm.v[par]; }
+    __device__ __forceinline__ Slot p(int par, int i) const { return sm.p[par][i]; }
+    __device__ __forceinline__ void put(Slot d, const uint32_t (&val)[8]) const {
 #pragma unroll
-    for (int k = 0; k < 8; k++) dst[k][lane] = v[k];
-}
-__device__ __forceinline__ void sm_get(uint32_t* v, const uint32_t (*src)[32], int lane) {
+        for (int k = 0; k < 8; k++) d[k][lane] = val[k];
+    }
+    __device__ __forceinline__ void get(uint32_t (&val)[8], Slot s) const {
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = src[k][lane];
-}
+        for (int k = 0; k < 8; k++) val[k] = s[k][lane];
+    }
+    static __device__ __forceinline__ void arrive(int id, int count) {
+        asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
+    static __device__ __forceinline__ void wait(int id, int count) {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void block() const { __syncthreads(); }
+    __device__ __forceinline__ void z_arrive(int par) const { arrive(BAR_Z + par, 32 * (T + 1)); }
+    __device__ __forceinline__ void z_wait(int par) const { wait(BAR_Z + par, 32 * (T + 1)); }
+    __device__ __forceinline__ void v_arrive(int par) const { arrive(BAR_V + par, 64); }
+    __device__ __forceinline__ void v_wait(int par) const { wait(BAR_V + par, 64); }
+    __device__ __forceinline__ void p_arrive(int par) const { arrive(BAR_P + par, 32 * T); }
+    __device__ __forceinline__ void p_wait(int par) const { wait(BAR_P + par, 32 * T); }
+    __device__ __forceinline__ void pro_arrive() const { arrive(BAR_PRO, 32 * T); }
+    __device__ __forceinline__ void pro_wait() const { wait(BAR_PRO, 32 * T); }
+};
 
-__global__ void __launch_bounds__(32 * T, 1)
+__global__ void __launch_bounds__(32 * COOP_WARPS, 1)
 tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
                        uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     using L = Layout<T>;
     constexpr int A = T - 1;
     extern __shared__ __align__(16) unsigned char coop_raw[];
-    CoopSmem& sm = *reinterpret_cast<CoopSmem*>(coop_raw);
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t h = (uint64_t)blockIdx.x * 32 + lane;
-    const bool live = h < n_out;          // dead lanes run along on zeros (barriers are block wide)
+    CoopBus bus{*reinterpret_cast<CoopSmem*>(coop_raw), (int)(threadIdx.x & 31)};
+    const int w = threadIdx.x >> 5;
+    const int role = w == COOP_CHAIN_WARP ? 0 : (w == 0 ? COOP_CHAIN_WARP : w);
+    const uint64_t h = (uint64_t)blockIdx.x * 32 + bus.lane;
+    const bool live = h < n_out;          // dead lanes run along on zeros (barriers count whole warps)
     const uint32_t* tbl = c_tbl;
 
-    // ---- absorb: warp w >= 1 takes child w-1 of its hash ---------------------
+    // ---- absorb: role i in 1..T-1 takes child i-1 of its hash ------------------
     uint32_t s[8];
-    if (w == 0) {
+    if (role == 0) {
 #pragma unroll
         for (int k = 0; k < 8; k++) s[k] = tbl[L::S0 * 8 + k];
-    } else {
+    } else if (role < T) {
         uint32_t wd[8], raw[8];
-        const uint64_t j = h * A + (w - 1);
+        const uint64_t j = h * A + (role - 1);
         if (live && j >= shift && j - shift < n_in) {
             load_node(wd, in + 2 * (j - shift));
         } else {
@@ -144,135 +163,15 @@ tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_
             for (int k = 0; k < 8; k++) wd[k] = zero.w[k];
         }
         words_to_limbs<false>(raw, wd);
-        absorb<T>(s, raw, w, tbl);
-    }
-
-    uint32_t xs[T + 1][8];
-    // ---- first half: rounds 0..3 -----------------------------------------------
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::PRE_M) * 8;
-        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::PRE_V) * 8;
-        uint32_t x[8];
-        sbox(x, s);
-        sm_put(sm.x[r & 1][w], x, lane);
-        __syncthreads();
+        absorb<T>(s, raw, role, tbl);
+    } else {
 #pragma unroll
-        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[r & 1][i], lane);
-        dot<T, 8>(s, &xs[0][0], m + w * T * 8, v + w * 8);
+        for (int k = 0; k < 8; k++) s[k] = 0;
     }
-
-    // ---- partial rounds ------------------------------------------------------------
-    // Pair j, buffers of parity j & 1.  Two barriers per pair:
-    //   before (A): warp 0 publishes x_a; warp w >= 1 publishes s_w*rowA[w] and s_w*rowB[w]
-    //   before (B): warp 0 forms n = x_a*m00 + k_A + sum pa, publishes x_b = n^5;
-    //               warp 1 publishes c_B*x_a
-    //   after  (B): warp 0 forms s_0 = x_b*m00' + k_B + sum pb + cx;
-    //               warp w >= 1 updates s_w += w_A x_a + w_B x_b  and runs ahead into pair j+1
-    // A buffer of parity p is rewritten in pair j+2 only by warps that have passed
-    // barrier (B) of pair j+1, which its readers of pair j reach after reading it.
-#pragma unroll 1
-    for (int j = 0; j < L::N_PAIRS; j++) {
-        const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
-        const int p = j & 1;
-        if (w == 0) {
-            uint32_t xa[8], xb[8], n[8], t[8];
-            sbox(xa, s);                                              // round A
-            sm_put(sm.xa[p], xa, lane);
-            __syncthreads();                                          // (A)
-            mont_mul_add(n, xa, pt, pt + T * 8);                      // x_a*m00 + k_A
-#pragma unroll
-            for (int i = 1; i < T; i++) {
-                sm_get(t, sm.pa[p][i], lane);
-                add8(n, n, t);
-                csub2p(n);
-            }
-            sbox(xb, n);                                              // round B
-            sm_put(sm.xb[p], xb, lane);
-            __syncthreads();                                          // (B)
-            mont_mul_add(s, xb, pt + (T + 1) * 8, pt + (2 * T + 2) * 8);   // x_b*m00' + k_B
-#pragma unroll
-            for (int i = 1; i < T; i++) {
-                sm_get(t, sm.pb[p][i], lane);
-                add8(s, s, t);
-                csub2p(s);
-            }
-            sm_get(t, sm.cx[p], lane);
-            add8(s, s, t);
-            csub2p(s);
-        } else {
-            uint32_t t[8], ab[2][8];
-            mont_mul(t, s, pt + w * 8);                               // s_w * rowA[w]
-            sm_put(sm.pa[p][w], t, lane);
-            mont_mul(t, s, pt + (T + 1 + w) * 8);                     // s_w * rowB[w]
-            sm_put(sm.pb[p][w], t, lane);
-            __syncthreads();                                          // (A)
-            sm_get(ab[0], sm.xa[p], lane);
-            if (w == 1) {
-                mont_mul(t, ab[0], pt + (2 * T + 1) * 8);             // c_B * x_a
-                sm_put(sm.cx[p], t, lane);
-            }
-            __syncthreads();                                          // (B)
-            sm_get(ab[1], sm.xb[p], lane);
-            dot<2, 8, false>(t, &ab[0][0], pt + (2 * T + 3 + 2 * (w - 1)) * 8, nullptr);
-            add8(s, s, t);
-            csub2p(s);
-        }
-    }
-    if (L::N_SINGLES > 0) {                                           // the odd round out, in the plain form
-        if (w > 0) sm_put(sm.s[w], s, lane);
-        __syncthreads();
-        const uint32_t* pt = tbl + L::SINGLES * 8;
-        if (w == 0) {
-            uint32_t n[8];
-#pragma unroll
-            for (int i = 1; i < T; i++) sm_get(xs[i], sm.s[i], lane);
-            sbox(xs[0], s);
-            sm_put(sm.xa[0], xs[0], lane);
-            __syncthreads();
-            dot<T, 8>(n, &xs[0][0], pt, pt + (2 * T - 1) * 8);
-#pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = n[k];
-        } else {
-            uint32_t xa[8], d[8];
-            __syncthreads();
-            sm_get(xa, sm.xa[0], lane);
-            mont_mul(d, xa, pt + (T + w - 1) * 8);
-            add8(s, s, d);
-            csub2p(s);
-        }
-    }
-    if (w > 0) {                                              // remaining constants of the first tail round
-        add8(s, s, tbl + (L::LAST_D + w - 1) * 8);
-        csub2p(s);
-    }
-
-    // ---- second half: 3 full rounds, then the output row -------------------------
-#pragma unroll 1
-    for (int r = 0; r < 3; r++) {
-        const uint32_t* m = tbl + L::FULL_M * 8;
-        const uint32_t* v = tbl + (L::TAIL_V + r * T) * 8;
-        uint32_t x[8];
-        sbox(x, s);
-        sm_put(sm.x[r & 1][w], x, lane);
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[r & 1][i], lane);
-        dot<T, 8>(s, &xs[0][0], m + w * T * 8, v + w * 8);
-    }
-    {
-        uint32_t x[8];
-        sbox(x, s);
-        sm_put(sm.x[1][w], x, lane);                          // rounds 0..2 left buffer 0 last
-        __syncthreads();
-    }
-    if (w == 0 && live) {
-#pragma unroll
-        for (int i = 0; i < T; i++) sm_get(xs[i], sm.x[1][i], lane);
-        uint32_t hsh[8], ow[8];
-        dot<T, 8>(hsh, &xs[0][0], tbl + L::OUT_ROW * 8, nullptr);
-        csub_p_exact(hsh);
-        csub_p_exact(hsh);
+    uint32_t hsh[8];
+    coop_hash<T>(hsh, s, role, bus, tbl);
+    if (role == 0 && live) {
+        uint32_t ow[8];
         limbs_to_words<false>(ow, hsh);
         store_node(out + 2 * h, ow);
     }
@@ -397,7 +296,7 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift
     memcpy(z.w, zero_be, 32);
     if (n_out <= coop_max()) {
         const unsigned grid = (unsigned)((n_out + 31) / 32);
-        tree_level_coop_kernel<<<grid, 32 * T, sizeof(CoopSmem), st>>>((const uint4*)d_in, shift, n_in,
+        tree_level_coop_kernel<<<grid, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((const uint4*)d_in, shift, n_in,
                                                                        (uint4*)d_out, n_out, z);
         return cudaGetLastError();
     }

@@ -82,7 +82,29 @@ def derive(t):
         # applies M first and B second, i.e. the product B.M
         N = _matmul(B, M)
     PRE = N
-    return dict(t=t, rf=rf, rp=rp, C=C, M=M, PRE=PRE, k=k, D=D, sparse=sparse)
+
+    # --- unit leading coefficient: carry s0 as u = s0 / lambda_j --------------------
+    # lambda_0 = 1, lambda_{j+1} = m00_j * lambda_j^5.  With z = u^5 (so s0^5 = lambda_j^5 z)
+    #     u'   = z + (v_j / lambda_{j+1}) . s[1:] + kv_j / lambda_{j+1}
+    #     s_i' = s_i + (w_j[i] * lambda_j^5) * z
+    # and after the last partial round s0 = lambda_RP * u, which the next full round
+    # only sees through s0^5 = lambda_RP^5 u^5: column 0 of that round's matrix is
+    # scaled instead (TAIL0).  One product less per partial round, and the S-box
+    # chain u -> u^2 -> u^4 -> u^5 -> u' has no multiplication after the S-box.
+    kv = lambda j: k[j + 1] if j + 1 < rp else D[0]
+    lam = [1]
+    scaled = []
+    for j in range(rp):
+        (row0, w) = sparse[j]
+        l5 = pow(lam[j], 5, P)
+        nxt = row0[0] * l5 % P
+        assert nxt != 0
+        inv_n = pow(nxt, P - 2, P)
+        scaled.append(([x * inv_n % P for x in row0[1:]], [x * l5 % P for x in w], kv(j) * inv_n % P))
+        lam.append(nxt)
+    l5 = pow(lam[rp], 5, P)
+    TAIL0 = [[M[i][0] * l5 % P] + list(M[i][1:]) for i in range(t)]
+    return dict(t=t, rf=rf, rp=rp, C=C, M=M, PRE=PRE, k=k, D=D, sparse=sparse, lam=lam, scaled=scaled, TAIL0=TAIL0)
 
 
 def hash_opt(inputs, tag=0, tables=None):
@@ -146,6 +168,46 @@ def hash_opt_paired(inputs, tag=0, tables=None):
         s = [new0] + [(s[i] + w[i - 1] * x0) % P for i in range(1, t)]
     s = [s[0]] + [(a + b) % P for a, b in zip(s[1:], T["D"][1:])]
     for r in range(4 + rp, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(a + b) % P for a, b in zip(s, C[r + 1])]
+    return s[0]
+
+
+def hash_opt_scaled(inputs, tag=0, tables=None, paired_rounds=True):
+    """The schedule the kernels run since round 2: partial rounds with the leading
+    coefficient scaled to one (see derive), taken in pairs when `paired_rounds`."""
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    rp, M, C = T["rp"], T["M"], T["C"]
+    sb = lambda x: pow(x, 5, P)
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    s = _matvec(T["PRE"], [sb(x) for x in s])
+    u = (s[0] + T["k"][0]) % P                              # lambda_0 = 1
+    rest = s[1:]
+    j = 0
+    if paired_rounds:
+        for jp in range(rp // 2):
+            (vA, wA, kA), (vB, wB, kB) = T["scaled"][2 * jp], T["scaled"][2 * jp + 1]
+            za = sb(u)
+            n = (za + sum(a * b for a, b in zip(vA, rest)) + kA) % P
+            zb = sb(n)
+            cB = sum(a * b for a, b in zip(vB, wA)) % P
+            u = (zb + sum(a * b for a, b in zip(vB, rest)) + cB * za + kB) % P
+            rest = [(rest[i] + wA[i] * za + wB[i] * zb) % P for i in range(t - 1)]
+        j = 2 * (rp // 2)
+    for j in range(j, rp):
+        v, w, kk = T["scaled"][j]
+        z = sb(u)
+        u = (z + sum(a * b for a, b in zip(v, rest)) + kk) % P
+        rest = [(rest[i] + w[i] * z) % P for i in range(t - 1)]
+    rest = [(a + b) % P for a, b in zip(rest, T["D"][1:])]
+    # first round of the second half: S-box on u itself, lambda_RP^5 sits in column 0 of TAIL0
+    s = _matvec(T["TAIL0"], [sb(u)] + [sb(x) for x in rest])
+    s = [(a + b) % P for a, b in zip(s, C[4 + rp + 1])]
+    for r in range(4 + rp + 1, 8 + rp):
         s = _matvec(M, [sb(x) for x in s])
         if r + 1 < 8 + rp:
             s = [(a + b) % P for a, b in zip(s, C[r + 1])]

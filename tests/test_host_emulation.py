@@ -139,33 +139,35 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
     for i in range(t):
         for j in range(t):
             assert el(k) == mont(T["PRE"][i][j]); k += 1
+    for i in range(t):
+        for j in range(t):
+            assert el(k) == mont(T["TAIL0"][i][j]); k += 1
     for r in range(3):
         for i in range(t):
             assert el(k) == vform(T["C"][r + 1][i]); k += 1
     assert el(k) == vform(T["k"][0]); k += 1
     for i in range(1, t):
         assert el(k) == 0; k += 1
-    kvf = lambda j: vform(T["k"][j + 1] if j + 1 < rp else T["D"][0])
     n_pairs = rp // 2 if opt_model.paired(t) else 0
     for jp in range(n_pairs):
-        (rowA, wA), (rowB, wB) = T["sparse"][2 * jp], T["sparse"][2 * jp + 1]
-        for i in range(t):
-            assert el(k) == mont(rowA[i]); k += 1
-        assert el(k) == kvf(2 * jp); k += 1
-        for i in range(t):
-            assert el(k) == mont(rowB[i]); k += 1
-        assert el(k) == mont(sum(a * b for a, b in zip(rowB[1:], wA)) % P); k += 1
-        assert el(k) == kvf(2 * jp + 1); k += 1
+        (vA, wA, kA), (vB, wB, kB) = T["scaled"][2 * jp], T["scaled"][2 * jp + 1]
+        for i in range(t - 1):
+            assert el(k) == mont(vA[i]); k += 1
+        assert el(k) == vform(kA); k += 1
+        for i in range(t - 1):
+            assert el(k) == mont(vB[i]); k += 1
+        assert el(k) == mont(sum(a * b for a, b in zip(vB, wA)) % P); k += 1
+        assert el(k) == vform(kB); k += 1
         for i in range(t - 1):
             assert el(k) == mont(wA[i]); k += 1
             assert el(k) == mont(wB[i]); k += 1
     for j in range(2 * n_pairs, rp):
-        row0, w = T["sparse"][j]
-        for i in range(t):
-            assert el(k) == mont(row0[i]); k += 1
+        v, w, kk = T["scaled"][j]
+        for i in range(t - 1):
+            assert el(k) == mont(v[i]); k += 1
         for i in range(t - 1):
             assert el(k) == mont(w[i]); k += 1
-        assert el(k) == kvf(j); k += 1
+        assert el(k) == vform(kk); k += 1
     for i in range(1, t):
         assert el(k) == mont(T["D"][i]); k += 1
     for r in range(3):
@@ -175,6 +177,9 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
         assert el(k) == T["M"][0][j]; k += 1
     for j in range(t):
         assert el(k) == mont(T["M"][0][j]); k += 1
+    for j in range(rp):
+        exp = 0 if j == 0 else sum(a * b for a, b in zip(T["scaled"][j][0], T["scaled"][j - 1][1])) % P
+        assert el(k) == mont(exp); k += 1
     assert k * 8 == words
 
 
@@ -192,4 +197,23 @@ def test_mont_sqr_equals_mul(emu):
         emu.hostemu_mont_mul(limbs(a), limbs(a), q)
         assert val(r) == val(q), hex(a)
         assert val(r) % P == a * a * RINV % P
+    assert emu.hostemu_overflow_count() == base
+
+
+@pytest.mark.parametrize("t", range(2, 9))
+def test_warp_cooperative_schedule_equals_oracle(emu, t):
+    """coop.cuh — the schedule of the kernel that takes the tree levels near the root —
+    run with one host thread per role over barriers that follow the PTX named-barrier
+    rules: same hash as the oracle, no barrier entered twice in a generation, no value
+    past 2^256, whichever role is the slow one."""
+    rng = random.Random(900 + t)
+    base = emu.hostemu_overflow_count()
+    cases = [[1] * (t - 1), [R - 1] * (t - 1), [P - 1] * (t - 1)] + [[rng.randrange(R) for _ in range(t - 1)] for _ in range(3)]
+    jitters = [0, 1, 1 << t, (1 << t) - 2, 2, (1 << (t + 1)) - 1 - 1]
+    for i, ins in enumerate(cases):
+        exp = O.poseidon_permute_hash([x % P for x in ins], 0)
+        buf = b"".join(x.to_bytes(32, "big") for x in ins)
+        out = ctypes.create_string_buffer(32)
+        assert emu.hostemu_coop_hash(t, buf, out, jitters[i % len(jitters)]) == 0
+        assert int.from_bytes(out.raw, "big") == exp, (t, i)
     assert emu.hostemu_overflow_count() == base

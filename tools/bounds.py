@@ -43,16 +43,17 @@ def run(t, rp):
     for r in range(4):                                       # first half
         x = [sbox(v, track) for v in s]
         s = [rs(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
-    for j in range(rp // 2):                                 # paired partial rounds
-        xa = sbox(s[0], track)
-        n = rs(track(dot([(xa, 1.0)] + [(si, 1.0) for si in s[1:]])))
-        xb = sbox(n, track)
-        n0 = rs(track(dot([(xb, 1.0)] + [(si, 1.0) for si in s[1:]] + [(xa, 1.0)])))
-        s = [n0] + [csub2p(track(si + track(dot([(xa, 1.0), (xb, 1.0)], 0)))) for si in s[1:]]
+    ri = csub2p if t >= 5 else (lambda x: x)                 # poseidon.cuh: RI = T >= 5
+    for j in range(rp // 2):                                 # paired partial rounds, unit leading coefficient
+        za = sbox(s[0], track)
+        n = csub2p(track(ri(track(dot([(si, 1.0) for si in s[1:]]))) + za))
+        zb = sbox(n, track)
+        n0 = csub2p(track(ri(track(dot([(si, 1.0) for si in s[1:]] + [(za, 1.0)]))) + zb))
+        s = [n0] + [csub2p(track(si + track(dot([(za, 1.0), (zb, 1.0)], 0)))) for si in s[1:]]
     for j in range(rp % 2):                                  # the odd round out
-        x0 = sbox(s[0], track)
-        n0 = rs(track(dot([(x0, 1.0)] + [(si, 1.0) for si in s[1:]])))
-        s = [n0] + [csub2p(track(si + track(dot([(x0, 1.0)], 0)))) for si in s[1:]]
+        z = sbox(s[0], track)
+        n0 = csub2p(track(ri(track(dot([(si, 1.0) for si in s[1:]]))) + z))
+        s = [n0] + [csub2p(track(si + track(dot([(z, 1.0)], 0)))) for si in s[1:]]
     s = [s[0]] + [csub2p(track(si + 1.0)) for si in s[1:]]
     for r in range(3):
         x = [sbox(v, track) for v in s]
