@@ -5,6 +5,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 // 128-thread blocks.  Resident blocks per SM (register cap): measured on B200
@@ -20,6 +21,32 @@
 #endif
 
 namespace inf {
+
+// Programmatic dependent launch for the level-after-level kernels of a tree: the next
+// level's grid is set up while the previous one drains (its blocks wait in
+// griddep_wait() before they touch the previous level's output), which takes the
+// launch gap (~4 us) off every latency-bound level.  INF_NO_PDL=1 disables it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                  cudaStream_t st, Args... args) {
+    static const bool pdl = !(getenv("INF_NO_PDL") && atoi(getenv("INF_NO_PDL")));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 struct TagArg {          // domain tag in wire order (poseidon.rs:110-120); has == 0 -> tag 0
     uint32_t w[8];

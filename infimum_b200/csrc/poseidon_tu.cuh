@@ -62,10 +62,12 @@ __global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
 tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
                   uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     constexpr int A = T - 1;
+    griddep_launch_dependents();
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_out) return;
     uint32_t iw[A][8], ow[8];
     const uint64_t first = idx * A;
+    griddep_wait();                         // the level below is complete and visible
 #pragma unroll
     for (int i = 0; i < A; i++) {
         const uint64_t j = first + i;
@@ -142,6 +144,7 @@ tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_
     constexpr int A = T - 1;
     extern __shared__ __align__(16) unsigned char coop_raw[];
     CoopBus bus{*reinterpret_cast<CoopSmem*>(coop_raw), (int)(threadIdx.x & 31)};
+    griddep_launch_dependents();
     const int w = threadIdx.x >> 5;
     const int role = w == COOP_CHAIN_WARP ? 0 : (w == 0 ? COOP_CHAIN_WARP : w);
     const uint64_t h = (uint64_t)blockIdx.x * 32 + bus.lane;
@@ -156,6 +159,7 @@ tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_
     } else if (role < T) {
         uint32_t wd[8], raw[8];
         const uint64_t j = h * A + (role - 1);
+        griddep_wait();                     // the level below is complete and visible
         if (live && j >= shift && j - shift < n_in) {
             load_node(wd, in + 2 * (j - shift));
         } else {
@@ -245,6 +249,22 @@ static int occupancy_pad() {
     return pad;
 }
 
+// A tree level whose grid is a little more than 3 blocks per SM would run its last
+// few blocks alone, at single-warp latency, after everything else has finished; if
+// 4 or 5 blocks per SM hold the whole grid, let them (94 registers allow 5).
+static int level_pad(unsigned grid) {
+    static int sms[64] = {};
+    const int pad = occupancy_pad();
+    if (T > 3 || pad != 74 * 1024) return pad;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return pad;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    const unsigned n = (unsigned)sms[dev];
+    if (grid <= 3 * n || grid > 5 * n) return pad;
+    return grid <= 4 * n ? 55 * 1024 : 44 * 1024;
+}
+
 
 cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, uint64_t n,
                                                 const TagArg& tag, bool le, cudaStream_t st) {
@@ -296,13 +316,12 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift
     memcpy(z.w, zero_be, 32);
     if (n_out <= coop_max()) {
         const unsigned grid = (unsigned)((n_out + 31) / 32);
-        tree_level_coop_kernel<<<grid, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((const uint4*)d_in, shift, n_in,
-                                                                       (uint4*)d_out, n_out, z);
-        return cudaGetLastError();
+        return launch_chained(tree_level_coop_kernel, grid, 32 * COOP_WARPS, sizeof(CoopSmem), st, (const uint4*)d_in,
+                              shift, n_in, (uint4*)d_out, n_out, z);
     }
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
-    tree_level_kernel<<<grid, INF_BLOCK, occupancy_pad(), st>>>((const uint4*)d_in, shift, n_in, (uint4*)d_out, n_out, z);
-    return cudaGetLastError();
+    return launch_chained(tree_level_kernel, grid, INF_BLOCK, level_pad(grid), st, (const uint4*)d_in, shift, n_in,
+                          (uint4*)d_out, n_out, z);
 }
 
 cudaError_t INF_CAT(launch_path_root_t, INF_T)(const void* d_idx, const void* d_leaves,
