@@ -15,6 +15,9 @@
  *   - The caller owns every buffer; the library keeps no pointer after return.
  *   - Calls on one inf_ctx must be serialised by the caller (like `&mut self`,
  *     pallet/src/hash/poseidon.rs:78); distinct contexts are independent.
+ *   - Device pointers handed to `_dev` calls must be 16-byte aligned (the kernels
+ *     move nodes with 128-bit loads and stores); a misaligned pointer is refused
+ *     with INF_ERR_BAD_ALIGNMENT before anything is launched.
  *   - Host-buffer calls are synchronous.  `_dev` calls take device pointers,
  *     enqueue on the given CUDA stream (a cudaStream_t passed as void*; NULL =
  *     the context's own non-blocking stream, so pass cudaStreamLegacy /
@@ -52,6 +55,9 @@ extern "C" {
 #define INF_ERR_NULL_POINTER 24
 #define INF_ERR_BAD_ARITY 25
 #define INF_ERR_BAD_DEPTH 26
+#define INF_ERR_BUFFER_TOO_SMALL 27 /* an output array (frontier entries) has too few slots */
+#define INF_ERR_BAD_FRONTIER 28     /* not a state insert() can leave behind (state.rs:176-225) */
+#define INF_ERR_BAD_ALIGNMENT 29    /* device pointers must be 16-byte aligned (128-bit loads) */
 /* device */
 #define INF_ERR_NO_DEVICE 64
 #define INF_ERR_CUDA 65
@@ -202,11 +208,53 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
  * completed the tree (state.rs:218-222), the root (then the frontier is empty).
  *   out_levels   cap bytes, out_hashes cap*32 bytes; cap >= 4*33 always suffices
  *   n_entries    number of frontier entries written
- * Errors: TREE_ALREADY_FULL if more leaves than arity^full_depth. */
+ * Errors: TREE_ALREADY_FULL if more leaves than arity^full_depth; BUFFER_TOO_SMALL
+ * if the frontier has more than `cap` entries. */
 int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepend_blank_leaf,
                       const uint8_t* leaves, uint64_t n_leaves, uint8_t* out_levels,
                       uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
                       uint32_t* insert_depth, int* has_root, uint8_t root[32]);
+
+/* ---- the stored tree: insert and merge on a persisted frontier -----------------------
+ * The pallet persists `PollStateTree {depth, count, hashes, root}` after every
+ * extrinsic (pallet/src/lib.rs:706-714) and the next insert / merge starts from it.
+ * These two calls are that pair on the stored state, so a node never needs the
+ * leaf history:
+ *
+ * inf_tree_append = `insert(leaf)` for every leaf of a batch (state.rs:176-225)
+ * applied to a tree whose frontier is (in_levels[i], in_hashes[i]), i < n_in, and
+ * whose `depth` field is depth_in.  A fresh interaction tree is the empty frontier;
+ * a fresh registration tree is the one-entry frontier (0, zeroes[0]) that
+ * PollStateTree::new seeds (state.rs:150-158, 48-52).  Outputs as inf_tree_frontier:
+ * the new frontier (highest level first), the new `depth`, and — if the batch
+ * completed the tree (state.rs:218-222) — *has_root = 1 with the root and an empty
+ * frontier.  `count` is the caller's: count_in + n_leaves.
+ * Errors: TREE_ALREADY_FULL if the leaves do not fit arity^full_depth (nothing is
+ * hashed; the reference would fail at the first leaf that does not fit — insert
+ * the fitting prefix first to mirror that); BAD_FRONTIER if the input is not a
+ * frontier insert() can leave (levels non-increasing, fewer than `arity` entries per
+ * level, all below full_depth); BUFFER_TOO_SMALL if cap is short (4*33 always suffices).
+ * The `_dev` form takes the leaves from device memory (e.g. straight from
+ * inf_interaction_leaves_dev) and orders its work after `stream`'s.
+ *
+ * inf_tree_merge_frontier = `merge(to_depth)` (state.rs:230-281) on that frontier:
+ * trailing runs of equal level are padded with the level's zero and hashed upwards
+ * until one entry is left (and, with to_depth, until it sits at full_depth).
+ * *has_root = 0 and INF_OK for an empty frontier (root stays None, state.rs:240-248).
+ * The work is a chain of at most ~full_depth dependent hashes — latency, not
+ * throughput: the bulk of a tree is hashed by inf_tree_append / inf_tree_merge. */
+int inf_tree_append(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels,
+                    const uint8_t* in_hashes, uint32_t n_in, uint32_t depth_in, const uint8_t* leaves,
+                    uint64_t n_leaves, uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap,
+                    uint32_t* n_entries, uint32_t* depth_out, int* has_root, uint8_t root[32]);
+int inf_tree_append_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels,
+                        const uint8_t* in_hashes, uint32_t n_in, uint32_t depth_in, const void* d_leaves,
+                        uint64_t n_leaves, uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap,
+                        uint32_t* n_entries, uint32_t* depth_out, int* has_root, uint8_t root[32],
+                        void* stream);
+int inf_tree_merge_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* levels,
+                            const uint8_t* hashes, uint32_t n, int to_depth, uint8_t root[32], int* has_root,
+                            uint32_t* root_depth);
 
 /* ---- retained trees and Merkle paths ------------------------------------------------
  * inf_tree_build keeps every level of the dense, zero-padded tree of `depth`

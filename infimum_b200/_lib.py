@@ -26,6 +26,9 @@ ERR_INVALID_WIDTH_CIRCOM = 19
 ERR_NULL_POINTER = 24
 ERR_BAD_ARITY = 25
 ERR_BAD_DEPTH = 26
+ERR_BUFFER_TOO_SMALL = 27
+ERR_BAD_FRONTIER = 28
+ERR_BAD_ALIGNMENT = 29
 ERR_NO_DEVICE = 64
 ERR_CUDA = 65
 ERR_OUT_OF_MEMORY = 66
@@ -44,6 +47,7 @@ EXPORTS = [
     "inf_multi_device_count", "inf_multi_tree_merge", "inf_multi_poseidon_hash_batch", "inf_merge_registrations",
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
     "inf_measure_imad_peak", "inf_poseidon_hash_batch_params",
+    "inf_tree_append", "inf_tree_append_dev", "inf_tree_merge_frontier",
 ]
 
 _lib = None
@@ -110,6 +114,14 @@ def load() -> C.CDLL:
     lib.inf_tree_frontier.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_uint64, vp, vp, C.c_uint32, u32p,
                                       u32p, ip, vp]
     lib.inf_tree_frontier.restype = C.c_int
+    lib.inf_tree_append.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, vp,
+                                    C.c_uint32, u32p, u32p, ip, vp]
+    lib.inf_tree_append.restype = C.c_int
+    lib.inf_tree_append_dev.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp,
+                                        vp, C.c_uint32, u32p, u32p, ip, vp, vp]
+    lib.inf_tree_append_dev.restype = C.c_int
+    lib.inf_tree_merge_frontier.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int, vp, ip, u32p]
+    lib.inf_tree_merge_frontier.restype = C.c_int
     lib.inf_tree_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_uint64, C.POINTER(vp)]
     lib.inf_tree_build.restype = C.c_int
     lib.inf_tree_root.argtypes = [vp, vp]

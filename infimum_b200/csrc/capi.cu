@@ -45,6 +45,7 @@ struct inf_ctx {
     size_t scratch_bytes[2] = {0, 0};
     void* io[2] = {nullptr, nullptr};          // staging for host-buffer calls
     size_t io_bytes[2] = {0, 0};
+    void* d_front = nullptr;                   // frontier entries on the device: 33 levels x 4 nodes (+ 1 scratch node)
     uint32_t* d_dense[14] = {};
     uint8_t zeroes[2][33][32];                 // [0] binary, [1] quinary (zeroes.rs)
     std::string last_cuda_error;
@@ -117,9 +118,9 @@ TagArg make_tag(const uint8_t* tag) {
 }
 
 cudaError_t launch_level(uint32_t arity, const void* in, uint64_t shift, uint64_t n_in, void* out,
-                         uint64_t n_out, const uint8_t* zero, cudaStream_t st) {
-    return arity == 2 ? launch_tree_level_t3(in, shift, n_in, out, n_out, zero, st)
-                      : launch_tree_level_t6(in, shift, n_in, out, n_out, zero, st);
+                         uint64_t n_out, const uint8_t* zero, cudaStream_t st, const void* prefix = nullptr) {
+    return arity == 2 ? launch_tree_level_t3(in, prefix, shift, n_in, out, n_out, zero, st)
+                      : launch_tree_level_t6(in, prefix, shift, n_in, out, n_out, zero, st);
 }
 
 // arity^e saturating at 2^64-1
@@ -299,6 +300,133 @@ int rows_pipeline(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* 
     return INF_OK;
 }
 
+
+// ---- stored frontiers (`PollStateTree.hashes`, state.rs:85-86) ---------------------------------
+constexpr uint32_t FRONT_NODES = 33 * 4;      // at most arity - 1 <= 4 entries per level, levels 0..32
+
+inline bool misaligned(const void* p) { return ((uintptr_t)p & 15) != 0; }
+
+int ensure_front(inf_ctx* ctx) {
+    if (!ctx->d_front) CU(cudaMalloc(&ctx->d_front, (FRONT_NODES + 1) * 32));
+    return INF_OK;
+}
+
+// Entries per level (levels must not increase towards the tail, fewer than `arity` per level,
+// all below full_depth) and the number of leaves the frontier stands for.
+int parse_frontier(uint32_t arity, uint32_t full_depth, const uint8_t* levels, uint32_t n, uint32_t cnt[33],
+                   uint64_t* n_leaves) {
+    for (int l = 0; l < 33; l++) cnt[l] = 0;
+    unsigned __int128 total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t l = levels[i];
+        if (l > 32 || l >= full_depth + (n == 1 ? 1u : 0u) || (i && l > levels[i - 1])) return INF_ERR_BAD_FRONTIER;
+        if (++cnt[l] >= arity) return INF_ERR_BAD_FRONTIER;
+        total += pow_sat(arity, l);
+    }
+    if (total > (unsigned __int128)UINT64_MAX) return INF_ERR_BAD_FRONTIER;
+    *n_leaves = (uint64_t)total;
+    return INF_OK;
+}
+
+// The insert cascade of state.rs:176-225 for a whole batch: frontier in + leaves -> frontier out.
+// Appending leaves is an addition in base `arity`: at every level the pending nodes are the
+// frontier's entries at that level (they open the first, incomplete group) followed by the
+// nodes the level below produced; every full group of `arity` becomes a parent, the remainder
+// is the new frontier at that level.  Only full groups are hashed (no zero padding): that is
+// merge's business.  Leaves come from host memory (h_leaves) or device memory (d_leaves).
+int tree_append_core(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels,
+                     const uint8_t* in_hashes, uint32_t n_in, uint32_t depth_in, const uint8_t* h_leaves,
+                     const void* d_leaves, uint64_t n_leaves, uint8_t* out_levels, uint8_t* out_hashes,
+                     uint32_t cap, uint32_t* n_entries, uint32_t* depth_out, int* has_root, uint8_t root[32],
+                     cudaStream_t st) {
+    *n_entries = 0;
+    if (depth_out) *depth_out = depth_in;
+    if (has_root) *has_root = 0;
+    uint32_t cnt[33];
+    uint64_t n_old = 0;
+    int rc = parse_frontier(arity, full_depth, in_levels, n_in, cnt, &n_old);
+    if (rc) return rc;
+    const uint64_t capacity = pow_sat(arity, full_depth);
+    if (n_old > capacity || n_leaves > capacity - n_old) return INF_ERR_TREE_ALREADY_FULL;   // insert(): state.rs:182
+    // frontier entries by level, in order; `first[l]` = index of level l's first entry
+    uint32_t first[34];
+    {
+        uint32_t at = n_in;
+        for (int l = 0; l <= 33; l++) {                 // levels are stored highest first
+            first[l] = l < 33 ? at - cnt[l] : 0;
+            if (l < 33) at -= cnt[l];
+        }
+    }
+    std::vector<std::vector<uint8_t>> tails(33);        // new frontier per level
+    int stop = -1;                                       // levels above `stop` keep their input entries
+    uint32_t depth = depth_in;
+    bool completed = false;
+    uint8_t root_local[32];
+    if (n_leaves) {
+        if ((rc = ensure_front(ctx))) return rc;
+        const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+        // device copy of the input frontier, level l at node 4 l
+        std::vector<uint8_t> packed(FRONT_NODES * 32, 0);
+        for (int l = 0; l < 33; l++)
+            for (uint32_t k = 0; k < cnt[l]; k++) memcpy(&packed[(4 * l + k) * 32], in_hashes + (size_t)(first[l] + k) * 32, 32);
+        if (n_in) CU(cudaMemcpyAsync(ctx->d_front, packed.data(), packed.size(), cudaMemcpyHostToDevice, st));
+        const char* cur;
+        if (h_leaves) {
+            if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32))) return rc;
+            CU(cudaMemcpyAsync(ctx->io[0], h_leaves, (size_t)n_leaves * 32, cudaMemcpyHostToDevice, st));
+            cur = (const char*)ctx->io[0];
+        } else {
+            cur = (const char*)d_leaves;
+        }
+        const uint64_t n1 = (n_leaves + 4) / arity + 1, n2 = n1 / arity + 2;
+        if ((rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
+        if ((rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
+        uint64_t n_cur = n_leaves;
+        for (uint32_t l = 0;; l++) {
+            if (l == full_depth) {                       // the cascade reached the top: n_old + n_leaves == capacity
+                CU(cudaMemcpyAsync(root_local, cur, 32, cudaMemcpyDeviceToHost, st));
+                completed = true;
+                stop = 32;
+                break;
+            }
+            const uint64_t pc = cnt[l], total = pc + n_cur, n_par = total / arity, rem = total % arity;
+            tails[l].resize(rem * 32);
+            for (uint64_t k = 0; k < rem; k++) {
+                const uint64_t idx = total - rem + k;
+                if (idx < pc) memcpy(&tails[l][k * 32], in_hashes + (size_t)(first[l] + idx) * 32, 32);
+                else CU(cudaMemcpyAsync(&tails[l][k * 32], cur + (idx - pc) * 32, 32, cudaMemcpyDeviceToHost, st));
+            }
+            stop = (int)l;
+            if (n_par == 0) break;
+            char* dst = (char*)ctx->scratch[l & 1];
+            CU(launch_level(arity, cur, pc, n_par * arity - pc, dst, n_par, Z[l], st,
+                            pc ? (const char*)ctx->d_front + (size_t)4 * l * 32 : nullptr));
+            depth = std::max(depth, l + 1);              // state.rs:212-213
+            cur = dst;
+            n_cur = n_par;
+        }
+        CU(cudaStreamSynchronize(st));
+    }
+    if (depth_out) *depth_out = depth;
+    if (completed) {                                     // state.rs:218-222: root set, frontier cleared
+        if (has_root) *has_root = 1;
+        if (root) memcpy(root, root_local, 32);
+        return INF_OK;
+    }
+    uint32_t n = 0;
+    for (int l = 32; l >= 0; l--) {
+        const uint32_t k_n = l > stop ? cnt[l] : (uint32_t)(tails[l].size() / 32);
+        for (uint32_t k = 0; k < k_n; k++) {
+            if (n >= cap || !out_levels || !out_hashes) return INF_ERR_BUFFER_TOO_SMALL;
+            out_levels[n] = (uint8_t)l;
+            memcpy(out_hashes + 32 * n, l > stop ? in_hashes + (size_t)(first[l] + k) * 32 : &tails[l][k * 32], 32);
+            n++;
+        }
+    }
+    *n_entries = n;
+    return INF_OK;
+}
+
 std::mutex g_init_mu;
 
 }  // namespace
@@ -321,6 +449,9 @@ const char* inf_strerror(int code) {
         case INF_ERR_NULL_POINTER: return "null pointer argument";
         case INF_ERR_BAD_ARITY: return "arity must be 2 or 5";
         case INF_ERR_BAD_DEPTH: return "tree depth exceeds the 33-level zero table";
+        case INF_ERR_BUFFER_TOO_SMALL: return "output buffer too small";
+        case INF_ERR_BAD_FRONTIER: return "frontier is not a state insert() can leave behind";
+        case INF_ERR_BAD_ALIGNMENT: return "device pointer must be 16-byte aligned";
         case INF_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
         case INF_ERR_CUDA: return "CUDA error (see inf_last_cuda_error)";
         case INF_ERR_OUT_OF_MEMORY: return "device out of memory";
@@ -411,6 +542,7 @@ void inf_destroy(inf_ctx* ctx) {
             if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
             if (ctx->io[i]) cudaFree(ctx->io[i]);
         }
+        if (ctx->d_front) cudaFree(ctx->d_front);
         for (int t = 0; t < 14; t++)
             if (ctx->d_dense[t]) cudaFree(ctx->d_dense[t]);
         for (int i = 0; i < 3; i++) {
@@ -427,6 +559,7 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
                                 void* d_out, void* stream) {
     int rc = check_hash_args(ctx, n_inputs, d_in, n, d_out);
     if (rc) return rc;
+    if (misaligned(d_in) || misaligned(d_out)) return INF_ERR_BAD_ALIGNMENT;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     return hash_batch_dev(ctx, n_inputs, flags, domain_tag, d_in, n, d_out,
@@ -575,6 +708,7 @@ int inf_registration_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const v
                                 uint64_t n, void* d_leaves, void* stream) {
     if (!ctx) return INF_ERR_NULL_POINTER;
     if (n && (!d_public_keys || !d_timestamps || !d_leaves)) return INF_ERR_NULL_POINTER;
+    if (misaligned(d_public_keys) || misaligned(d_leaves) || ((uintptr_t)d_timestamps & 7)) return INF_ERR_BAD_ALIGNMENT;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(launch_registration_leaves(d_public_keys, d_timestamps, d_leaves, n,
@@ -586,6 +720,7 @@ int inf_interaction_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const vo
                                uint64_t n, void* d_leaves, void* stream) {
     if (!ctx) return INF_ERR_NULL_POINTER;
     if (n && (!d_public_keys || !d_data || !d_leaves)) return INF_ERR_NULL_POINTER;
+    if (misaligned(d_public_keys) || misaligned(d_data) || misaligned(d_leaves)) return INF_ERR_BAD_ALIGNMENT;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(launch_interaction_leaves(d_public_keys, d_data, d_leaves, n, stream ? (cudaStream_t)stream : ctx->stream));
@@ -608,6 +743,7 @@ int inf_tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pr
                        int to_depth, const void* d_leaves, uint64_t n_leaves, uint8_t root[32],
                        uint32_t* insert_depth, uint32_t* root_depth, int* has_root, void* stream) {
     if (!ctx) return INF_ERR_NULL_POINTER;
+    if (misaligned(d_leaves)) return INF_ERR_BAD_ALIGNMENT;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, d_leaves, n_leaves,
@@ -646,6 +782,7 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
     if (n_in && !d_in) return INF_ERR_NULL_POINTER;
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (level_in + n_levels > 32) return INF_ERR_BAD_DEPTH;
+    if (misaligned(d_in) || misaligned(d_out)) return INF_ERR_BAD_ALIGNMENT;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -689,71 +826,92 @@ int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int pre
     if (n_leaves && !leaves) return INF_ERR_NULL_POINTER;
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (full_depth > 32) return INF_ERR_BAD_DEPTH;
-    *n_entries = 0;
-    if (insert_depth) *insert_depth = 0;
-    if (has_root) *has_root = 0;
-    const uint64_t shift = prepend_blank_leaf ? 1 : 0;
-    const uint64_t n_total = n_leaves + shift;
-    const uint64_t capacity = pow_sat(arity, full_depth);
-    if (n_total > capacity) return INF_ERR_TREE_ALREADY_FULL;
-    if (n_total == 0) return INF_OK;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    // PollStateTree::new seeds `hashes` with the blank leaf (state.rs:150-158): a frontier of one entry
+    const uint8_t lvl0 = 0;
+    const uint8_t* z0 = ctx->zeroes[arity == 2 ? 0 : 1][0];
+    return tree_append_core(ctx, arity, full_depth, &lvl0, z0, prepend_blank_leaf ? 1 : 0, 0, leaves, nullptr,
+                            n_leaves, out_levels, out_hashes, cap, n_entries, insert_depth, has_root, root,
+                            ctx->stream);
+}
+
+int inf_tree_append(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels,
+                    const uint8_t* in_hashes, uint32_t n_in, uint32_t depth_in, const uint8_t* leaves,
+                    uint64_t n_leaves, uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap,
+                    uint32_t* n_entries, uint32_t* depth_out, int* has_root, uint8_t root[32]) {
+    if (!ctx || !n_entries) return INF_ERR_NULL_POINTER;
+    if ((n_leaves && !leaves) || (n_in && (!in_levels || !in_hashes))) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    return tree_append_core(ctx, arity, full_depth, in_levels, in_hashes, n_in, depth_in, leaves, nullptr, n_leaves,
+                            out_levels, out_hashes, cap, n_entries, depth_out, has_root, root, ctx->stream);
+}
+
+int inf_tree_append_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels,
+                        const uint8_t* in_hashes, uint32_t n_in, uint32_t depth_in, const void* d_leaves,
+                        uint64_t n_leaves, uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap,
+                        uint32_t* n_entries, uint32_t* depth_out, int* has_root, uint8_t root[32],
+                        void* stream) {
+    if (!ctx || !n_entries) return INF_ERR_NULL_POINTER;
+    if ((n_leaves && !d_leaves) || (n_in && (!in_levels || !in_hashes))) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    if (misaligned(d_leaves)) return INF_ERR_BAD_ALIGNMENT;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    return tree_append_core(ctx, arity, full_depth, in_levels, in_hashes, n_in, depth_in, nullptr, d_leaves, n_leaves,
+                            out_levels, out_hashes, cap, n_entries, depth_out, has_root, root,
+                            stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int inf_tree_merge_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* levels,
+                            const uint8_t* hashes, uint32_t n, int to_depth, uint8_t root[32], int* has_root,
+                            uint32_t* root_depth) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!levels || !hashes)) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (full_depth > 32) return INF_ERR_BAD_DEPTH;
+    if (has_root) *has_root = 0;
+    if (root_depth) *root_depth = 0;
+    uint64_t n_old = 0;
+    uint32_t cnt[33];
+    int rc = parse_frontier(arity, full_depth, levels, n, cnt, &n_old);
+    if (rc) return rc;
+    if (n == 0) return INF_OK;                                     // merge on an empty frontier: root stays None
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    if ((rc = ensure_front(ctx))) return rc;
     cudaStream_t st = ctx->stream;
-    int rc;
-    if (n_leaves) {
-        if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32))) return rc;
-        CU(cudaMemcpyAsync(ctx->io[0], leaves, (size_t)n_leaves * 32, cudaMemcpyHostToDevice, st));
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    char* E = (char*)ctx->d_front;
+    char* tmp = E + FRONT_NODES * 32;
+    CU(cudaMemcpyAsync(E, hashes, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    // PollStateTree::merge (state.rs:240-271): hash the trailing run of equal-level entries, padded
+    // with that level's zero, into one entry a level up, until a single entry is left (and, with
+    // to_depth, until it sits at full_depth).  Each step consumes the previous one's output: a
+    // chain of at most ~full_depth single hashes, enqueued back to back without host round trips.
+    std::vector<uint8_t> lv(levels, levels + n);
+    for (;;) {
+        const uint8_t d = lv.back();
+        if (lv.size() == 1 && (!to_depth || d == full_depth)) break;
+        if (d >= 32 || d >= full_depth) return INF_ERR_BAD_FRONTIER;
+        size_t size = 0;
+        while (size < lv.size() && lv[lv.size() - 1 - size] == d) size++;
+        const size_t i = lv.size() - size;
+        CU(launch_level(arity, E + i * 32, 0, size, tmp, 1, Z[d], st));
+        CU(cudaMemcpyAsync(E + i * 32, tmp, 32, cudaMemcpyDeviceToDevice, st));
+        lv.resize(i);
+        lv.push_back((uint8_t)(d + 1));
     }
-    // Full nodes only: level d has floor(n_total / arity^d) of them; the
-    // frontier keeps the trailing (that count mod arity) of each level — the
-    // base-arity digits of n_total — highest level first.
-    struct Lvl { const char* nodes; uint64_t n_full; uint64_t sh; };
-    std::vector<Lvl> lv;
-    const uint64_t n1 = n_total / arity, n2 = n1 / arity;
-    if ((rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], std::max<uint64_t>(n1, 1) * 32))) return rc;
-    if ((rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], std::max<uint64_t>(n2, 1) * 32))) return rc;
-    // every level's trailing nodes are copied out as soon as the level exists
-    std::vector<uint8_t> tail_levels;
-    std::vector<std::vector<uint8_t>> tails;      // per level, digit * 32 bytes
-    const char* cur = (const char*)ctx->io[0];
-    uint64_t n_cur = n_total, sh = shift;         // n_cur counts logical nodes (shift included)
-    uint32_t d = 0;
-    for (;; d++) {
-        const uint64_t digit = n_cur % arity, n_next = n_cur / arity;
-        std::vector<uint8_t> t(digit * 32);
-        for (uint64_t k = 0; k < digit; k++) {
-            const uint64_t j = n_cur - digit + k;           // logical index at this level
-            if (j < sh) memcpy(&t[k * 32], Z[d], 32);       // the blank leaf itself (level 0 only)
-            else CU(cudaMemcpyAsync(&t[k * 32], cur + (j - sh) * 32, 32, cudaMemcpyDeviceToHost, st));
-        }
-        tails.push_back(std::move(t));
-        if (n_next == 0) break;
-        char* dst = (char*)ctx->scratch[d & 1];
-        CU(launch_level(arity, cur, sh, n_cur - sh, dst, n_next, Z[d], st));   // reads only the first arity*n_next logical nodes
-        cur = dst;
-        n_cur = n_next;
-        sh = 0;
-    }
+    uint8_t r[32];
+    CU(cudaMemcpyAsync(r, E, 32, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    uint32_t idepth = d;                                    // highest level reached by the cascade
-    if (insert_depth) *insert_depth = idepth;
-    if (n_total == capacity) {                              // completed by insert: root, empty frontier
-        if (has_root) *has_root = 1;
-        if (root) memcpy(root, tails.back().data(), 32);
-        return INF_OK;
-    }
-    uint32_t n = 0;
-    for (int l = (int)tails.size() - 1; l >= 0; l--) {
-        for (size_t k = 0; k * 32 < tails[l].size(); k++) {
-            if (n >= cap || !out_levels || !out_hashes) return INF_ERR_NULL_POINTER;
-            out_levels[n] = (uint8_t)l;
-            memcpy(out_hashes + 32 * n, &tails[l][k * 32], 32);
-            n++;
-        }
-    }
-    *n_entries = n;
+    if (root) memcpy(root, r, 32);
+    if (has_root) *has_root = 1;
+    if (root_depth) *root_depth = lv[0];
     return INF_OK;
 }
 

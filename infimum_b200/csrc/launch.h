@@ -25,15 +25,21 @@ namespace inf {
 // Programmatic dependent launch for the level-after-level kernels of a tree: the next
 // level's grid is set up while the previous one drains (its blocks wait in
 // griddep_wait() before they touch the previous level's output), which takes the
-// launch gap (~4 us) off every latency-bound level.  INF_NO_PDL=1 disables it.
+// launch gap (~3 us) off a latency-bound level.  Only for grids of at most one block
+// per SM (`early`): blocks of a larger grid that become resident early sit wherever a
+// slot happened to be free, and the level then runs on a lopsided placement — measured
+// on B200, chaining the wide levels made a 2^20-leaf tree 0.44 ms SLOWER, chaining the
+// levels near the root only makes a 2^10-leaf tree 0.03 ms faster
+// (profiles/r02_tree_levels.md).  INF_NO_PDL=1 disables it.
 #ifdef __CUDACC__
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_chained(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
-                                  cudaStream_t st, Args... args) {
-    static const bool pdl = !(getenv("INF_NO_PDL") && atoi(getenv("INF_NO_PDL")));
+                                  cudaStream_t st, bool early, Args... args) {
+    static const bool pdl_on = !(getenv("INF_NO_PDL") && atoi(getenv("INF_NO_PDL")));
+    const bool pdl = pdl_on && early;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
@@ -57,8 +63,9 @@ struct TagArg {          // domain tag in wire order (poseidon.rs:110-120); has 
     cudaError_t upload_table_t##N(const uint32_t* host_tbl, size_t words);                          \
     cudaError_t launch_hash_batch_t##N(const void* d_in, void* d_out, uint64_t n, const TagArg& tag, \
                                        bool le, cudaStream_t st);                                   \
-    cudaError_t launch_tree_level_t##N(const void* d_in, uint64_t shift, uint64_t n_in, void* d_out, \
-                                       uint64_t n_out, const uint8_t* zero_be, cudaStream_t st);    \
+    cudaError_t launch_tree_level_t##N(const void* d_in, const void* d_prefix, uint64_t shift,      \
+                                       uint64_t n_in, void* d_out, uint64_t n_out,                  \
+                                       const uint8_t* zero_be, cudaStream_t st);                    \
     cudaError_t launch_path_root_t##N(const void* d_idx, const void* d_leaves, const void* d_paths,  \
                                       uint32_t depth, void* d_roots, uint64_t n, cudaStream_t st);
 INF_DECLARE_WIDTH(2)

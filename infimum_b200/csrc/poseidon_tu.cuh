@@ -53,13 +53,16 @@ hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_
 }
 
 // One level of an arity-(T-1) Merkle tree over big-endian 32-byte nodes.
-// The level's logical node array is `shift` copies of the zero value followed
-// by in[0..n_in): shift = 1 at level 0 of the registration tree, whose leaf 0
-// is the blank state leaf = zeroes[0] (state.rs:48-52), else 0.
+// The level's logical node array is `shift` leading nodes followed by
+// in[0..n_in).  The leading nodes are prefix[0..shift) if `prefix` is given —
+// the entries a stored frontier holds at this level, which open the first,
+// incomplete group when leaves are appended to it (state.rs:176-225) — else
+// copies of the zero value: shift = 1 at level 0 of the registration tree,
+// whose leaf 0 is the blank state leaf = zeroes[0] (state.rs:48-52).
 // out[i] = H(node[A*i], ..., node[A*i+A-1]); nodes past the end are the
 // level's zero value (PollStateTree::merge's right padding, state.rs:262-266).
 __global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
-tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
+tree_level_kernel(const uint4* __restrict__ in, const uint4* __restrict__ prefix, uint64_t shift, uint64_t n_in,
                   uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     constexpr int A = T - 1;
     griddep_launch_dependents();
@@ -73,6 +76,8 @@ tree_level_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
         const uint64_t j = first + i;
         if (j >= shift && j - shift < n_in) {
             load_node(iw[i], in + 2 * (j - shift));
+        } else if (j < shift && prefix) {
+            load_node(iw[i], prefix + 2 * j);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; k++) iw[i][k] = zero.w[k];
@@ -138,7 +143,7 @@ struct CoopBus {
 };
 
 __global__ void __launch_bounds__(32 * COOP_WARPS, 1)
-tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_in,
+tree_level_coop_kernel(const uint4* __restrict__ in, const uint4* __restrict__ prefix, uint64_t shift, uint64_t n_in,
                        uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     using L = Layout<T>;
     constexpr int A = T - 1;
@@ -162,6 +167,8 @@ tree_level_coop_kernel(const uint4* __restrict__ in, uint64_t shift, uint64_t n_
         griddep_wait();                     // the level below is complete and visible
         if (live && j >= shift && j - shift < n_in) {
             load_node(wd, in + 2 * (j - shift));
+        } else if (live && j < shift && prefix) {
+            load_node(wd, prefix + 2 * j);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; k++) wd[k] = zero.w[k];
@@ -308,7 +315,7 @@ cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t word
     return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
 }
 
-cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift, uint64_t n_in,
+cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, const void* d_prefix, uint64_t shift, uint64_t n_in,
                                                 void* d_out, uint64_t n_out,
                                                 const uint8_t* zero_be, cudaStream_t st) {
     if (n_out == 0) return cudaSuccess;
@@ -316,12 +323,13 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, uint64_t shift
     memcpy(z.w, zero_be, 32);
     if (n_out <= coop_max()) {
         const unsigned grid = (unsigned)((n_out + 31) / 32);
-        return launch_chained(tree_level_coop_kernel, grid, 32 * COOP_WARPS, sizeof(CoopSmem), st, (const uint4*)d_in,
-                              shift, n_in, (uint4*)d_out, n_out, z);
+        return launch_chained(tree_level_coop_kernel, grid, 32 * COOP_WARPS, sizeof(CoopSmem), st, grid <= 128,
+                              (const uint4*)d_in,
+                              (const uint4*)d_prefix, shift, n_in, (uint4*)d_out, n_out, z);
     }
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
-    return launch_chained(tree_level_kernel, grid, INF_BLOCK, level_pad(grid), st, (const uint4*)d_in, shift, n_in,
-                          (uint4*)d_out, n_out, z);
+    return launch_chained(tree_level_kernel, grid, INF_BLOCK, level_pad(grid), st, false, (const uint4*)d_in,
+                          (const uint4*)d_prefix, shift, n_in, (uint4*)d_out, n_out, z);
 }
 
 cudaError_t INF_CAT(launch_path_root_t, INF_T)(const void* d_idx, const void* d_leaves,

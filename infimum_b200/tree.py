@@ -10,9 +10,12 @@ and the two callers that define the contract, pallet/src/poll/provider.rs:
 
 The reference inserts one leaf per extrinsic and keeps only the frontier; the
 GPU path is the batch equivalent: leaves are buffered host-side by `insert`
-(or handed over in bulk with `extend`) and the whole tree is reduced on the
-device by `merge`.  `merge` returns a tree that is field-for-field what the
-reference would hold: {depth, count, root, hashes: []}.
+(or handed over in bulk with `extend`) and folded into the stored frontier on
+the device in one go (`inf_tree_append`) when the frontier is asked for; a tree
+that still is what `new` made is reduced by `merge` in one shot
+(`inf_tree_merge`), any other from its frontier (`inf_tree_merge_frontier`).
+Either way the result is field-for-field what the reference would hold:
+{depth, count, root, hashes}.
 """
 from __future__ import annotations
 
@@ -43,6 +46,11 @@ def empty_ballot_roots() -> List[bytes]:
 
 
 class PollStateTree:
+    """Field-for-field the reference struct (state.rs:70-91).  What has been hashed
+    in so far is held the way the pallet stores it — the frontier `hashes` — plus
+    a buffer of leaves not yet folded in, so a tree can be resumed from persisted
+    state (`from_state`) and never needs its leaf history."""
+
     def __init__(self, arity: int, full_depth: int, zero_hash: Optional[Tuple[int, bytes]] = None,
                  ctx: Optional[Context] = None):
         self.arity = int(arity)
@@ -51,14 +59,21 @@ class PollStateTree:
         self.count = 0
         self.root: Optional[bytes] = None
         self.ctx = ctx or get_context()
-        # state.rs:150-158: an optional pre-seeded (level, hash) entry.  The
-        # reference only ever seeds level 0 with zeroes[0] (state.rs:48-52).
-        self._seed = zero_hash
+        # state.rs:150-158: an optional pre-seeded (level, hash) entry.  The reference only ever
+        # seeds level 0 with zeroes[0] (state.rs:48-52); that case also has a one-shot merge.
+        self._frontier: List[Tuple[int, bytes]] = []
+        self._blank = False
+        self._fresh = True                   # frontier is still what new() made
         if zero_hash is not None:
-            lvl, h = zero_hash
-            if lvl != 0 or bytes(h) != get_merkle_zeroes(self.arity, self.ctx)[0]:
-                raise ValueError("only the reference's seeding (level 0, zeroes[0]) is supported")
+            lvl, h = int(zero_hash[0]), bytes(zero_hash[1])
+            if len(h) != 32:
+                raise ValueError("hash must be 32 bytes")
+            self._frontier = [(lvl, h)]
+            self._blank = lvl == 0 and h == get_merkle_zeroes(self.arity, self.ctx)[0]
+            self._fresh = self._blank
         self._chunks: List[np.ndarray] = []
+        self._pending = 0
+        self._depth_before_pending = 0
 
     # -- reference constructor name
     @classmethod
@@ -66,32 +81,62 @@ class PollStateTree:
             ctx: Optional[Context] = None) -> "PollStateTree":
         return cls(arity, full_depth, zero_hash, ctx)
 
-    @property
-    def hashes(self) -> List[Tuple[int, bytes]]:
-        """The frontier `PollStateTree.hashes` (state.rs:85-86): empty once
-        `root` is set; before that, the (level, hash) pairs the reference's
-        insert cascade would have left, computed on the device from the
-        buffered leaves (inf_tree_frontier)."""
-        if self.root is not None:
-            return []
-        lv = self._leaves()
-        cap = 4 * 33
-        levels = C.create_string_buffer(cap)
-        hashes = C.create_string_buffer(cap * 32)
-        n, idepth, has = C.c_uint32(), C.c_uint32(), C.c_int()
-        root = C.create_string_buffer(32)
-        rc = self.ctx.lib.inf_tree_frontier(self.ctx.handle, self.arity, self.full_depth,
-                                            1 if self._seed is not None else 0,
-                                            lv.ctypes.data if lv.size else None, lv.shape[0], levels, hashes, cap,
-                                            C.byref(n), C.byref(idepth), C.byref(has), root)
-        self.ctx.check(rc)
-        return [(levels.raw[i], hashes.raw[32 * i:32 * i + 32]) for i in range(n.value)]
+    @classmethod
+    def from_state(cls, arity: int, full_depth: int, depth: int, count: int,
+                   hashes: Sequence[Tuple[int, bytes]], root: Optional[bytes] = None,
+                   ctx: Optional[Context] = None) -> "PollStateTree":
+        """Resume from the persisted struct (what the pallet reads back from storage,
+        lib.rs:706-714): insert / merge continue from the stored frontier."""
+        t = cls(arity, full_depth, None, ctx)
+        t.depth, t.count = int(depth), int(count)
+        t.root = bytes(root) if root is not None else None
+        t._frontier = [(int(l), bytes(h)) for l, h in hashes]
+        t._fresh = False
+        t._depth_before_pending = t.depth
+        return t
+
+    def _logical(self) -> int:
+        """Leaves the frontier stands for (the blank leaf included)."""
+        return sum(self.arity ** l for l, _ in self._frontier)
 
     def _total(self) -> int:
-        return self.count + (1 if self._seed is not None else 0)
+        return self._logical() + self._pending
+
+    def _flush(self):
+        """Fold the buffered leaves into the frontier (inf_tree_append)."""
+        if not self._pending:
+            return
+        lv = self._leaves()
+        n_in = len(self._frontier)
+        cap = 4 * 33
+        in_levels = bytes(l for l, _ in self._frontier)
+        in_hashes = b"".join(h for _, h in self._frontier)
+        levels = C.create_string_buffer(cap)
+        hashes = C.create_string_buffer(cap * 32)
+        n, depth, has = C.c_uint32(), C.c_uint32(), C.c_int()
+        root = C.create_string_buffer(32)
+        rc = self.ctx.lib.inf_tree_append(self.ctx.handle, self.arity, self.full_depth, in_levels, in_hashes, n_in,
+                                          self._depth_before_pending, lv.ctypes.data, lv.shape[0], levels, hashes, cap,
+                                          C.byref(n), C.byref(depth), C.byref(has), root)
+        self.ctx.check(rc)
+        self._frontier = [(levels.raw[i], hashes.raw[32 * i:32 * i + 32]) for i in range(n.value)]
+        self._chunks, self._pending, self._fresh = [], 0, False
+        self.depth = depth.value
+        self._depth_before_pending = self.depth
+        if has.value:
+            self.root = root.raw
+
+    @property
+    def hashes(self) -> List[Tuple[int, bytes]]:
+        """The frontier `PollStateTree.hashes` (state.rs:85-86): empty once `root` is
+        set; before that, the (level, hash) pairs the reference's insert cascade leaves."""
+        if self.root is not None:
+            return []
+        self._flush()
+        return list(self._frontier)
 
     def insert(self, leaf: bytes) -> "PollStateTree":
-        """state.rs:176-225 (buffers the leaf; hashing happens in merge)."""
+        """state.rs:176-225 (buffers the leaf; hashing happens in batches)."""
         if self.root is not None:
             raise MerkleTreeError("TreeAlreadyFull")
         if len(leaf) != 32:
@@ -107,19 +152,25 @@ class PollStateTree:
         cap = self.arity ** self.full_depth
         if self._total() + a.shape[0] > cap:
             raise MerkleTreeError("TreeAlreadyFull")
+        if not self._pending:
+            self._depth_before_pending = self.depth
         self._chunks.append(a)
+        self._pending += a.shape[0]
         self.count += a.shape[0]
         self._update_depth()
         if self._total() == cap:
             # insert() completes the tree by itself (state.rs:218-222)
-            self._reduce(to_depth=True, completing=True)
+            if self._fresh:
+                self._reduce(to_depth=True, completing=True)
+            else:
+                self._flush()
         return self
 
     def _update_depth(self):
         n, d = self._total(), 0
         while self.arity ** (d + 1) <= n and d < self.full_depth:
             d += 1
-        self.depth = d                                            # state.rs:212-213
+        self.depth = max(self.depth, d)                           # state.rs:212-213
 
     def _leaves(self) -> np.ndarray:
         if not self._chunks:
@@ -129,11 +180,12 @@ class PollStateTree:
         return self._chunks[0]
 
     def _reduce(self, to_depth: bool, completing: bool = False):
+        """One-shot new + insert x N + merge over the buffered leaves (fresh trees only)."""
         lv = self._leaves()
         root = C.create_string_buffer(32)
         idepth, rdepth, has = C.c_uint32(), C.c_uint32(), C.c_int()
         rc = self.ctx.lib.inf_tree_merge(self.ctx.handle, self.arity, self.full_depth,
-                                         1 if self._seed is not None else 0, 1 if to_depth else 0,
+                                         1 if self._blank else 0, 1 if to_depth else 0,
                                          lv.ctypes.data if lv.size else None, lv.shape[0], root,
                                          C.byref(idepth), C.byref(rdepth), C.byref(has))
         if rc == _lib.ERR_TREE_ALREADY_MERGED and completing:
@@ -141,15 +193,31 @@ class PollStateTree:
         self.ctx.check(rc)
         if has.value:
             self.root = root.raw
-            self._chunks = []
-        self.depth = idepth.value if self._total() else 0
+            self._chunks, self._pending, self._frontier = [], 0, []
+        self.depth = idepth.value
         return rdepth.value
 
     def merge(self, to_depth: bool) -> "PollStateTree":
         """state.rs:230-281"""
         if self.root is not None:
             raise MerkleTreeError("TreeAlreadyMerged")
-        self._reduce(to_depth)
+        if self._fresh:
+            self._reduce(to_depth)
+            return self
+        self._flush()
+        if self.root is not None:                               # cannot happen: extend() flushes on completion
+            return self
+        n = len(self._frontier)
+        root = C.create_string_buffer(32)
+        has, rdepth = C.c_int(), C.c_uint32()
+        rc = self.ctx.lib.inf_tree_merge_frontier(self.ctx.handle, self.arity, self.full_depth,
+                                                  bytes(l for l, _ in self._frontier),
+                                                  b"".join(h for _, h in self._frontier), n, 1 if to_depth else 0,
+                                                  root, C.byref(has), C.byref(rdepth))
+        self.ctx.check(rc)
+        if has.value:
+            self.root = root.raw
+            self._frontier = []
         return self
 
     @staticmethod

@@ -152,10 +152,51 @@ class FakeLib:
             _wr(root, t.root)
             return OK
         if len(t.hashes) > cap:
-            return E_NULL
+            return 27
         _wr(out_levels, bytes(l for l, _ in t.hashes))
         _wr(out_hashes, b"".join(h for _, h in t.hashes))
         _set(n_entries, len(t.hashes))
+        return OK
+
+    def inf_tree_append(self, ctx, arity, full_depth, in_levels, in_hashes, n_in, depth_in, leaves, n, out_levels,
+                        out_hashes, cap, n_entries, depth_out, has, root):
+        _set(n_entries, 0), _set(depth_out, depth_in), _set(has, 0)
+        lv, hs = _rd(in_levels, n_in), _rd(in_hashes, n_in * 32)
+        t = O.PollStateTree(arity=arity, full_depth=full_depth, depth=depth_in,
+                            hashes=[(lv[i], hs[32 * i:32 * i + 32]) for i in range(n_in)])
+        if sum(arity ** l for l in lv) + n > arity ** full_depth:
+            return FULL
+        data = _rd(leaves, n * 32)
+        for i in range(n):
+            t.insert(data[32 * i:32 * i + 32])
+        _set(depth_out, t.depth)
+        if t.root is not None:
+            _set(has, 1)
+            _wr(root, t.root)
+            return OK
+        if len(t.hashes) > cap:
+            return 27
+        _wr(out_levels, bytes(l for l, _ in t.hashes))
+        _wr(out_hashes, b"".join(h for _, h in t.hashes))
+        _set(n_entries, len(t.hashes))
+        return OK
+
+    def inf_tree_merge_frontier(self, ctx, arity, full_depth, levels, hashes, n, to_depth, root, has, rdepth):
+        _set(has, 0), _set(rdepth, 0)
+        lv, hs = _rd(levels, n), _rd(hashes, n * 32)
+        t = O.PollStateTree(arity=arity, full_depth=full_depth,
+                            hashes=[(lv[i], hs[32 * i:32 * i + 32]) for i in range(n)])
+        top = max(lv) if n else 0
+        t.merge(bool(to_depth))
+        if t.root is not None:
+            _set(has, 1)
+            _wr(root, t.root)
+            d = full_depth
+            if not to_depth:
+                d = top
+                while sum(arity ** l for l in lv) > arity ** d:
+                    d += 1
+            _set(rdepth, d)
         return OK
 
     # ---- leaves -------------------------------------------------------------------------

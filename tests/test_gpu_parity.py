@@ -381,6 +381,83 @@ def test_frontier_equals_insert_cascade(ib, arity, full_depth, blank):
         assert (t.depth, t.count) == (o.depth, o.count)
 
 
+def _resume(ib, o):
+    """A mirror tree resumed from the oracle tree's persisted fields."""
+    return ib.PollStateTree.from_state(o.arity, o.full_depth, o.depth, o.count, list(o.hashes), o.root)
+
+
+@pytest.mark.parametrize("arity,full_depth,blank", [(2, 12, True), (5, 5, False), (2, 12, False), (5, 5, True)])
+def test_insert_and_merge_on_a_stored_frontier(ib, arity, full_depth, blank):
+    """state.rs:176-281 on persisted state (lib.rs:706-714): resume from the frontier
+    after k inserts, append the rest in one batch, and get the oracle's incremental
+    state — frontier, depth, count — then merge from that frontier, both ways."""
+    import copy
+    allv = random_fr_bytes(900, seed=arity + 70)
+    rng = random.Random(arity * 100 + full_depth)
+    for n in [0, 1, 2, 5, 24, 25, 26, 124, 125, 126, 255, 256, 257, 624, 625, 626, 700, 900]:
+        splits = sorted({0, n, n // 2, rng.randrange(n + 1), rng.randrange(n + 1)})
+        o = O.PollStateTree.new(arity, full_depth, (0, O.merkle_zeroes(arity)[0]) if blank else None)
+        states = {}
+        for i in range(n + 1):
+            if i in splits:
+                states[i] = copy.deepcopy(o)
+            if i < n:
+                o.insert(allv[i].tobytes())
+        for k in splits:
+            t = _resume(ib, states[k]).extend(allv[k:n])
+            assert t.hashes == o.hashes, (arity, n, k)
+            assert (t.depth, t.count, t.root) == (o.depth, o.count, o.root), (arity, n, k)
+        for to_depth in (False, True):
+            m = copy.deepcopy(o).merge(to_depth)
+            t = _resume(ib, o).merge(to_depth)
+            assert (t.root, t.hashes, t.depth, t.count) == (m.root, m.hashes, m.depth, m.count), (arity, n, to_depth)
+
+
+@pytest.mark.parametrize("arity,full_depth", [(2, 6), (5, 3)])
+def test_stored_frontier_capacity_and_errors(ib, arity, full_depth):
+    import copy
+    import ctypes as C
+    cap = arity ** full_depth
+    allv = random_fr_bytes(cap + 1, seed=98)
+    for blank in (False, True):
+        n = cap - (1 if blank else 0)
+        o = O.PollStateTree.new(arity, full_depth, (0, O.merkle_zeroes(arity)[0]) if blank else None)
+        k = n // 3
+        for i in range(k):
+            o.insert(allv[i].tobytes())
+        mid = copy.deepcopy(o)
+        with pytest.raises(ib.MerkleTreeError) as e:            # one leaf too many: nothing is inserted
+            _resume(ib, mid).extend(allv[k:n + 1])
+        assert e.value.code == 1
+        for i in range(k, n):
+            o.insert(allv[i].tobytes())
+        t = _resume(ib, mid).extend(allv[k:n])                   # completed by insert (state.rs:218-222)
+        assert o.root is not None and (t.root, t.hashes, t.depth, t.count) == (o.root, [], o.depth, o.count)
+        with pytest.raises(ib.MerkleTreeError) as e:
+            t.merge(True)
+        assert e.value.code == 2
+    # malformed frontiers and short output arrays, at the C ABI
+    ctx = ib.get_context()
+    if not hasattr(ctx.lib, "_name"):
+        return                                                   # (the CPU stand-in does not model these)
+    h = allv[:8].tobytes()
+    out_l, out_h = C.create_string_buffer(8), C.create_string_buffer(8 * 32)
+    nn, dd, has = C.c_uint32(), C.c_uint32(), C.c_int()
+    root = C.create_string_buffer(32)
+
+    def append(levels, n_in, leaves, n, capn=8):
+        return ctx.lib.inf_tree_append(ctx.handle, arity, full_depth, bytes(levels), h, n_in, 0, leaves, n, out_l, out_h,
+                                       capn, C.byref(nn), C.byref(dd), C.byref(has), root)
+    lv = allv[4:10].tobytes()
+    assert append([0, 1], 2, lv, 1) == 28                       # levels must not increase towards the tail
+    assert append([1] * arity, arity, lv, 1) == 28              # a full group would have been hashed
+    assert append([full_depth, 0], 2, lv, 1) == 28
+    assert append([1, 0], 2, None, 0, capn=1) == 27
+    assert append([1, 0], 2, lv, 1) == 0 and nn.value >= 1
+    assert ctx.lib.inf_tree_merge_frontier(ctx.handle, arity, full_depth, bytes([0, 1]), h, 2, 0, root, C.byref(has),
+                                           C.byref(dd)) == 28
+
+
 def test_hypothesis_tree_and_reduction_properties(ib):
     """gpu_tree(leaves) == oracle insert*N + merge, and
     hash(x) == hash(x + p) for x < 2^256 - p, on hypothesis-drawn cases."""

@@ -40,6 +40,8 @@ test_participant_limit_reached_quirk = G.test_participant_limit_reached_quirk
 # trees, frontier, leaves, paths, custom parameters
 test_tree_capacity_edges = G.test_tree_capacity_edges
 test_frontier_equals_insert_cascade = G.test_frontier_equals_insert_cascade
+test_insert_and_merge_on_a_stored_frontier = G.test_insert_and_merge_on_a_stored_frontier
+test_stored_frontier_capacity_and_errors = G.test_stored_frontier_capacity_and_errors
 test_leaf_hashing_pins_and_oracle = G.test_leaf_hashing_pins_and_oracle
 test_verify_outcome_scenarios = G.test_verify_outcome_scenarios
 test_custom_parameters_equal_new_circom_for_the_circom_tables = G.test_custom_parameters_equal_new_circom_for_the_circom_tables

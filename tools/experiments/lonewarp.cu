@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I infimum_b200/csrc tools/experiments/lonewarp.cu -o tools/_bin/lonewarp
 #include <cstdio>
 #include <cuda_runtime.h>
+#include "fr_lat.cuh"
 #include "poseidon.cuh"
 using namespace inf;
 
@@ -20,6 +21,32 @@ __global__ void __launch_bounds__(128) k_chains(unsigned long long* out, unsigne
 #pragma unroll
             for (int k = 0; k < K; k++)
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((unsigned)acc[k]), "r"(b));
+    }
+    long long t1 = clock64();
+    unsigned long long x = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) x ^= acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// accumulate-only chains: the multiplicands do not depend on the accumulators
+template <int K>
+__global__ void __launch_bounds__(128) k_acc(unsigned long long* out, unsigned b, long long* cyc) {
+    unsigned long long acc[K];
+    unsigned a[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { acc[k] = threadIdx.x * 0x9e3779b97f4a7c15ull + k; a[k] = b * (k + 3) + threadIdx.x; }
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 4096; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a[k]), "r"(b));
+#pragma unroll
+        for (int k = 0; k < K; k++) a[k] += 0x9e37u;
     }
     long long t1 = clock64();
     unsigned long long x = 0;
@@ -47,6 +74,14 @@ __global__ void __launch_bounds__(128) k_prim(uint32_t* out, const uint32_t* in,
         if (OP == 3) dot<3, 8>(t, &x[0][0], in + 16, in + 8);
         if (OP == 4) dot<2, 8>(t, &x[0][0], in + 16, in + 8);
         if (OP == 5) { mont_mul(t, x[0], y); add8(t, t, x[1]); csub2p(t); }
+        if (OP == 6) mont_mul_lat(t, x[0], y);
+        if (OP == 7) mont_sqr_lat(t, x[0]);
+        if (OP == 8) sbox_lat(t, x[0]);
+        if (OP == 9) dot_lat<3, 8>(t, &x[0][0], in + 16, in + 8);
+        if (OP == 10) dot_lat<2, 8>(t, &x[0][0], in + 16, in + 8);
+        if (OP == 11) mont_mul_lat<1>(t, x[0], y);
+        if (OP == 12) mont_mul_lat<2>(t, x[0], y);
+        if (OP == 13) mont_mul_lat<3>(t, x[0], y);
         for (int i = 0; i < 8; i++) x[0][i] = t[i];
         x[0][7] &= 0x3fffffff;
     }
@@ -76,13 +111,21 @@ int main() {
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);                                                \
     printf("IMAD.WIDE, 1 warp per SMSP, %d independent chains: %.2f cycles per instruction\n", K, c / (4096.0 * 4 * K));
     CH(1) CH(2) CH(3) CH(4) CH(6) CH(8)
-    const char* names[] = {"mont_mul", "mont_sqr", "sbox (sqr, sqr, mul)", "dot<3> + csub2p", "dot<2> + csub2p", "mont_mul + add8 + csub2p"};
+#define AC(K)                                                                                      \
+    for (int rep = 0; rep < 2; rep++) k_acc<K><<<148, 128>>>(out64, 0x12345677u, cyc);             \
+    cudaDeviceSynchronize();                                                                       \
+    cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);                                                \
+    printf("IMAD.WIDE accumulate-only, 1 warp per SMSP, %d independent chains: %.2f cycles per instruction\n", K, c / (4096.0 * 4 * K));
+    AC(1) AC(2) AC(3) AC(4) AC(6) AC(8) AC(12)
+    const char* names[] = {"mont_mul", "mont_sqr", "sbox (sqr, sqr, mul)", "dot<3> + csub2p", "dot<2> + csub2p", "mont_mul + add8 + csub2p",
+                           "mont_mul_lat", "mont_sqr_lat", "sbox_lat", "dot_lat<3> + csub2p", "dot_lat<2> + csub2p",
+                           "mont_mul_lat<LEAD=1>", "mont_mul_lat<LEAD=2>", "mont_mul_lat<LEAD=3>"};
 #define PR(OP)                                                                     \
     for (int rep = 0; rep < 2; rep++) k_prim<OP><<<148, 128>>>(out, in, cyc);      \
     cudaDeviceSynchronize();                                                       \
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);                                \
     printf("lone warp, dependent %s: %.0f cycles\n", names[OP], c / 1000.0);
-    PR(0) PR(1) PR(2) PR(3) PR(4) PR(5)
+    PR(0) PR(1) PR(2) PR(3) PR(4) PR(5) PR(6) PR(7) PR(8) PR(9) PR(10) PR(11) PR(12) PR(13)
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
