@@ -271,6 +271,16 @@ int inf_tree_build(inf_ctx* ctx, uint32_t arity, uint32_t depth, int prepend_bla
                    const uint8_t* leaves, uint64_t n_leaves, inf_tree** out);
 int inf_tree_root(inf_tree* tree, uint8_t root[32]);
 int inf_tree_paths(inf_tree* tree, const uint64_t* leaf_indices, uint64_t n_idx, uint8_t* paths);
+/* The same for nodes of any level: paths from node_indices[i] of `level` up to the
+ * root, (depth - level) * (arity-1) * 32 bytes each, and the nodes themselves
+ * (all-zero subtrees to the right of the stored nodes read as zeroes[level]).
+ * With level = process_subtree_depth these are the batch subroots and the
+ * msgSubrootPathElements the coordinator feeds processMessages, one batch per index
+ * (circuits/process-messages.circom:57,85; cli/src/utils.ts:104-126), all batches
+ * in one call. */
+int inf_tree_node_paths(inf_tree* tree, uint32_t level, const uint64_t* node_indices, uint64_t n_idx,
+                        uint8_t* paths);
+int inf_tree_level_nodes(inf_tree* tree, uint32_t level, uint64_t first, uint64_t count, uint8_t* out);
 void inf_tree_destroy(inf_tree* tree);
 
 /* compute_merkle_root_from_path (provider.rs:396-436), batched: n paths of
@@ -299,6 +309,34 @@ int inf_multi_tree_merge(inf_multi* m, uint32_t arity, uint32_t full_depth, int 
 int inf_multi_poseidon_hash_batch(inf_multi* m, uint32_t n_inputs, uint32_t flags,
                                   const uint8_t* domain_tag, const uint8_t* in, uint64_t n,
                                   uint8_t* out);
+
+/* ---- replay: raw registrations / messages -> leaves -> merged tree on the device ------
+ * The reference's order of work for a poll is leaf hash -> insert -> merge
+ * (provider.rs:218-287, then 289-327).  These calls run that whole chain for a batch
+ * without the leaves leaving the device: the raw rows are uploaded in chunks, each
+ * chunk is leaf-hashed and its level-0 parents are formed on the same stream while
+ * the next chunk uploads, then the upper levels finish the tree.
+ *   inf_replay_registrations = register_participant x n + merge_registrations:
+ *       public_keys n*64, timestamps n*u64 -> registrations root (blank leaf first,
+ *       merge(false)), process commitment, `depth`
+ *   inf_replay_interactions  = consume_interaction x n + merge_interactions:
+ *       public_keys n*64, data n*320 -> interactions root (merge(true)), `depth`,
+ *       expected proof counts
+ *   leaves_out  optional host array (n*32) that receives the leaves
+ *   retained    optional: keeps every level on the device as an inf_tree of root-depth
+ *               levels for inf_tree_paths / inf_tree_node_paths; free with
+ *               inf_tree_destroy
+ * Errors as inf_tree_merge (TREE_ALREADY_FULL before any work if the rows do not
+ * fit; TREE_ALREADY_MERGED with the root written when they fill the tree exactly). */
+int inf_replay_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* public_keys,
+                             const uint64_t* timestamps, uint64_t n, uint8_t root[32],
+                             uint8_t process_commitment[32], uint32_t* insert_depth, uint8_t* leaves_out,
+                             inf_tree** retained);
+int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8_t* public_keys,
+                            const uint8_t* data, uint64_t n, uint32_t registrations_count,
+                            uint32_t process_subtree_depth, uint32_t tally_subtree_depth, uint8_t root[32],
+                            int* has_root, uint32_t* insert_depth, uint32_t* expected_process,
+                            uint32_t* expected_tally, uint8_t* leaves_out, inf_tree** retained);
 
 /* merge_registrations (provider.rs:289-311): inf_tree_merge(2, depth, 1, 0, ..)
  * followed by the process commitment H3(root, EMPTY_BALLOT_ROOTS[1], 0). */

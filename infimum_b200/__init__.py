@@ -9,7 +9,7 @@ reference interface over that ABI.  CUDA only: there is no CPU fallback.
 from .errors import DeviceError, MerkleTreeError, PoseidonError
 from .context import Context, get_context
 from .hasher import HASH_LEN, MAX_X5_LEN, MODULUS, Poseidon, PoseidonParameters
-from .leaves import interaction_leaves, registration_leaves
+from .leaves import interaction_leaves, registration_leaves, replay_interactions, replay_registrations
 from .paths import RetainedTree, compute_merkle_root_from_path, merkle_roots_from_paths, verify_outcome
 from .poll import Commitment, Poll, PollConfig
 from .tree import (PollStateTree, empty_ballot_roots, get_merkle_zeroes, merge_interactions,
@@ -19,6 +19,6 @@ __all__ = [
     "Context", "get_context", "Poseidon", "PoseidonParameters", "PollStateTree", "PoseidonError", "MerkleTreeError",
     "DeviceError", "MODULUS", "HASH_LEN", "MAX_X5_LEN", "get_merkle_zeroes", "empty_ballot_roots",
     "merge_registrations", "merge_interactions", "new_registration_tree", "new_interaction_tree",
-    "registration_leaves", "interaction_leaves", "Poll", "PollConfig", "Commitment",
+    "registration_leaves", "interaction_leaves", "replay_registrations", "replay_interactions", "Poll", "PollConfig", "Commitment",
     "RetainedTree", "compute_merkle_root_from_path", "merkle_roots_from_paths", "verify_outcome",
 ]

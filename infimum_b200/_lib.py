@@ -48,6 +48,7 @@ EXPORTS = [
     "inf_merge_interactions", "inf_debug_dense_params", "inf_debug_opt_table",
     "inf_measure_imad_peak", "inf_poseidon_hash_batch_params",
     "inf_tree_append", "inf_tree_append_dev", "inf_tree_merge_frontier",
+    "inf_tree_node_paths", "inf_tree_level_nodes", "inf_replay_registrations", "inf_replay_interactions",
 ]
 
 _lib = None
@@ -128,6 +129,15 @@ def load() -> C.CDLL:
     lib.inf_tree_root.restype = C.c_int
     lib.inf_tree_paths.argtypes = [vp, vp, C.c_uint64, vp]
     lib.inf_tree_paths.restype = C.c_int
+    lib.inf_tree_node_paths.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp]
+    lib.inf_tree_node_paths.restype = C.c_int
+    lib.inf_tree_level_nodes.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, vp]
+    lib.inf_tree_level_nodes.restype = C.c_int
+    lib.inf_replay_registrations.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint64, vp, vp, u32p, vp, C.POINTER(vp)]
+    lib.inf_replay_registrations.restype = C.c_int
+    lib.inf_replay_interactions.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, ip,
+                                            u32p, u32p, u32p, vp, C.POINTER(vp)]
+    lib.inf_replay_interactions.restype = C.c_int
     lib.inf_tree_destroy.argtypes = [vp]
     lib.inf_tree_destroy.restype = None
     lib.inf_merkle_roots_from_paths.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]

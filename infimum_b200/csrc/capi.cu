@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -166,19 +167,43 @@ int check_hash_args(inf_ctx* ctx, uint32_t n_inputs, const void* in, uint64_t n,
     return INF_OK;
 }
 
-// Core of the tree merge on device-resident leaves.  Leaves the root (if any)
-// in host memory.  `st` is synchronised before return.
-// If h_leaves is non-null the leaves are still in host memory and d_leaves is
-// the (uninitialised) device staging area for them: level 0 is then cut into
-// chunks that rotate over the three pipeline streams, each uploading its slice
-// of leaves and hashing it, so the upload hides behind the hashing.
+// Where level 0's input comes from when it is not on the device yet: fill(lo, hi, dst, ps,
+// slot) makes leaves [lo, hi) appear at dst (device memory) in stream order on ps, one of the
+// three pipeline streams (slot = its index, for per-stream staging).  Level 0 is then cut into
+// chunks of `chunk_out` parents that rotate over the pipeline streams, each producing its slice
+// of leaves and hashing it, so that uploads (and, for a replay from raw messages, the leaf
+// hashing) of one chunk hide behind the hashing of another.
+struct LeafFeed {
+    std::function<int(uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot)> fill;
+    uint64_t chunk_out = 1ull << 19;
+    uint8_t* leaves_out = nullptr;           // optional host copy of all leaves (n_leaves * 32 bytes)
+};
+
+int alloc_tree(inf_ctx* ctx, uint32_t arity, uint32_t depth, uint64_t shift, uint64_t n_leaves, inf_tree** out);
+
+// Leaves in host memory: one asynchronous upload per chunk.
+LeafFeed host_leaf_feed(inf_ctx* ctx, const uint8_t* h_leaves) {
+    LeafFeed f;
+    f.fill = [ctx, h_leaves](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int) -> int {
+        CU(cudaMemcpyAsync(dst, h_leaves + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ps));
+        return INF_OK;
+    };
+    return f;
+}
+
+// Core of the tree merge.  Leaves the root (if any) in host memory.  `st` is synchronised
+// before return.  Without a feed the leaves are already at d_leaves; with one, d_leaves is the
+// (uninitialised) device area they are produced into.  With `keep`, every level is retained in
+// a new inf_tree of root_depth levels (for Merkle paths) instead of ping-pong scratch; d_leaves
+// is then ignored unless there is no feed, in which case the leaves are copied from it.
 int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank, int to_depth,
                    const void* d_leaves, uint64_t n_leaves, uint8_t* root, uint32_t* insert_depth,
-                   uint32_t* root_depth, int* has_root, cudaStream_t st,
-                   const uint8_t* h_leaves = nullptr) {
+                   uint32_t* root_depth, int* has_root, cudaStream_t st, const LeafFeed* feed = nullptr,
+                   inf_tree** keep = nullptr) {
+    if (keep) *keep = nullptr;
     if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
     if (full_depth > 32) return INF_ERR_BAD_DEPTH;
-    if (n_leaves && !d_leaves) return INF_ERR_NULL_POINTER;
+    if (n_leaves && !d_leaves && !(feed && keep)) return INF_ERR_NULL_POINTER;
     const uint64_t shift = blank ? 1 : 0;
     const uint64_t n_total = n_leaves + shift;
     const uint64_t cap = pow_sat(arity, full_depth);
@@ -203,25 +228,59 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
     if (root_depth) *root_depth = rdepth;
 
     const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    int rc;
+    inf_tree* kt = nullptr;
+    LeafFeed copy_feed;
+    cudaError_t e0 = cudaSuccess;
+    if (keep) {
+        if ((rc = alloc_tree(ctx, arity, rdepth, shift, n_leaves, &kt))) return rc;
+        if (!feed) {                                               // device leaves: copy them into level 0
+            const char* src = (const char*)d_leaves;
+            copy_feed.fill = [ctx, src](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int) -> int {
+                CU(cudaMemcpyAsync(dst, src + lo * 32, (hi - lo) * 32, cudaMemcpyDeviceToDevice, ps));
+                return INF_OK;
+            };
+            feed = &copy_feed;
+        }
+        d_leaves = (char*)kt->d_nodes + shift * 32;
+        if (shift && (e0 = cudaMemcpyAsync(kt->d_nodes, Z[0], 32, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+            inf_tree_destroy(kt);
+            return cuda_fail(ctx, e0, "blank leaf");
+        }
+    }
+    auto bail = [&](int code) {
+        if (kt) inf_tree_destroy(kt);
+        return code;
+    };
+    // output of level l (the nodes of level l + 1)
+    auto level_dst = [&](uint32_t l) -> char* {
+        return kt ? (char*)kt->d_nodes + kt->offsets[l + 1] * 32 : (char*)ctx->scratch[l & 1];
+    };
     uint8_t root_local[32];
+    cudaError_t e = cudaSuccess;
+#define CUB(call)                                                         \
+    do {                                                                  \
+        if ((e = (call)) != cudaSuccess) return bail(cuda_fail(ctx, e, #call)); \
+    } while (0)
     if (rdepth == 0) {
         // single node: the blank leaf itself, or the only leaf
+        if (!blank && feed && (rc = feed->fill(0, 1, (char*)d_leaves, st, 0))) return bail(rc);
         if (blank) memcpy(root_local, Z[0], 32);
-        else if (h_leaves) memcpy(root_local, h_leaves, 32);
-        else CU(cudaMemcpyAsync(root_local, d_leaves, 32, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        else CUB(cudaMemcpyAsync(root_local, d_leaves, 32, cudaMemcpyDeviceToHost, st));
+        if (feed && feed->leaves_out && n_leaves) CUB(cudaMemcpyAsync(feed->leaves_out, d_leaves, 32, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
     } else {
         const uint64_t n1 = (n_total + arity - 1) / arity;
         const uint64_t n2 = (n1 + arity - 1) / arity;
-        int rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32);
-        if (rc) return rc;
-        rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32);
-        if (rc) return rc;
+        if (!kt) {
+            if ((rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
+            if ((rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
+        }
         const void* cur = d_leaves;
         uint64_t n_cur = n_leaves, sh = shift;
         uint32_t l_first = 0;
-        if (h_leaves) {
-            const uint64_t chunk_out = 1ull << 19;
+        if (feed) {
+            const uint64_t chunk_out = feed->chunk_out;
             int k = 0;
             for (uint64_t o0 = 0; o0 < n1; o0 += chunk_out, k++) {
                 const uint64_t o1 = std::min<uint64_t>(o0 + chunk_out, n1);
@@ -229,34 +288,41 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
                 const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
                 cudaStream_t ps = ctx->pipe[k % 3];
                 char* dl = (char*)d_leaves + leaf_lo * 32;
-                if (leaf_hi > leaf_lo)
-                    CU(cudaMemcpyAsync(dl, h_leaves + leaf_lo * 32, (leaf_hi - leaf_lo) * 32,
-                                       cudaMemcpyHostToDevice, ps));
-                CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo,
-                                (char*)ctx->scratch[0] + o0 * 32, o1 - o0, Z[0], ps));
+                if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return bail(rc);
+                CUB(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, level_dst(0) + o0 * 32, o1 - o0,
+                                 Z[0], ps));
             }
             for (int i = 0; i < 3; i++) {
-                CU(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
-                CU(cudaStreamWaitEvent(st, ctx->pipe_done[i], 0));
+                CUB(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
+                CUB(cudaStreamWaitEvent(st, ctx->pipe_done[i], 0));
             }
-            cur = ctx->scratch[0];
+            if (feed->leaves_out && n_leaves) {
+                // all leaves exist once every pipeline stream is through: read them back on pipe[0]
+                // while `st` hashes the upper levels
+                for (int i = 1; i < 3; i++) CUB(cudaStreamWaitEvent(ctx->pipe[0], ctx->pipe_done[i], 0));
+                CUB(cudaMemcpyAsync(feed->leaves_out, d_leaves, (size_t)n_leaves * 32, cudaMemcpyDeviceToHost, ctx->pipe[0]));
+            }
+            cur = level_dst(0);
             n_cur = n1;
             sh = 0;
             l_first = 1;
         }
         for (uint32_t l = l_first; l < rdepth; l++) {
             const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
-            void* dst = ctx->scratch[l & 1];
-            CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[l], st));
+            void* dst = level_dst(l);
+            CUB(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[l], st));
             cur = dst;
             n_cur = n_next;
             sh = 0;
         }
-        CU(cudaMemcpyAsync(root_local, cur, 32, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CUB(cudaMemcpyAsync(root_local, cur, 32, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
+        if (feed && feed->leaves_out) CUB(cudaStreamSynchronize(ctx->pipe[0]));
     }
+#undef CUB
     if (root) memcpy(root, root_local, 32);
     if (has_root) *has_root = 1;
+    if (keep) *keep = kt;
     return completed_by_insert ? INF_ERR_TREE_ALREADY_MERGED : INF_OK;   // merge(): state.rs:236
 }
 
@@ -424,6 +490,55 @@ int tree_append_core(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const ui
         }
     }
     *n_entries = n;
+    return INF_OK;
+}
+
+// rows [lo, hi) of two host arrays -> per-stream staging -> leaf kernel -> dst
+template <class Launch>
+LeafFeed raw_rows_feed(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* in1, size_t row1, uint32_t arity,
+                       uint64_t chunk_out, Launch launch) {
+    LeafFeed f;
+    f.chunk_out = chunk_out;
+    const size_t slot_rows = (size_t)chunk_out * arity;
+    f.fill = [=](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot) -> int {
+        char* s0 = (char*)ctx->io[0] + (size_t)slot * slot_rows * (row0 + row1);
+        char* s1 = s0 + slot_rows * row0;
+        CU(cudaMemcpyAsync(s0, in0 + lo * row0, (hi - lo) * row0, cudaMemcpyHostToDevice, ps));
+        CU(cudaMemcpyAsync(s1, in1 + lo * row1, (hi - lo) * row1, cudaMemcpyHostToDevice, ps));
+        CU(launch(s0, s1, dst, hi - lo, ps));
+        return INF_OK;
+    };
+    return f;
+}
+
+// A retained tree: every level 0..depth of the dense zero-padded tree, back to back on the device.
+int alloc_tree(inf_ctx* ctx, uint32_t arity, uint32_t depth, uint64_t shift, uint64_t n_leaves, inf_tree** out) {
+    inf_tree* t = new inf_tree();
+    t->ctx = ctx; t->arity = arity; t->depth = depth; t->shift = shift; t->n_leaves = n_leaves;
+    uint64_t total_nodes = 0, c = n_leaves + shift;
+    for (uint32_t l = 0; l <= depth; l++) {
+        t->offsets.push_back(total_nodes);
+        t->counts.push_back(c);
+        total_nodes += c;
+        c = (c + arity - 1) / arity;
+    }
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    cudaError_t e;
+    auto fail = [&](const char* what) {
+        inf_tree_destroy(t);
+        return cuda_fail(ctx, e, what);
+    };
+    if ((e = cudaMalloc(&t->d_nodes, total_nodes * 32)) != cudaSuccess) return fail("cudaMalloc tree levels");
+    if ((e = cudaMalloc(&t->d_level_ptrs, (depth + 1) * sizeof(void*))) != cudaSuccess) return fail("cudaMalloc");
+    if ((e = cudaMalloc(&t->d_level_counts, (depth + 1) * 8)) != cudaSuccess) return fail("cudaMalloc");
+    if ((e = cudaMalloc(&t->d_zero_nodes, 33 * 32)) != cudaSuccess) return fail("cudaMalloc");
+    std::vector<void*> ptrs;
+    for (uint32_t l = 0; l <= depth; l++) ptrs.push_back((char*)t->d_nodes + t->offsets[l] * 32);
+    // synchronous copies of a few hundred bytes: the host arrays above do not outlive this call
+    if ((e = cudaMemcpy(t->d_level_ptrs, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy");
+    if ((e = cudaMemcpy(t->d_level_counts, t->counts.data(), t->counts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy");
+    if ((e = cudaMemcpy(t->d_zero_nodes, Z, 33 * 32, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy");
+    *out = t;
     return INF_OK;
 }
 
@@ -771,8 +886,9 @@ int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int prepen
         int rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], (size_t)n_leaves * 32);
         if (rc) return rc;
     }
+    const LeafFeed feed = host_leaf_feed(ctx, leaves);
     return tree_merge_dev(ctx, arity, full_depth, prepend_blank_leaf, to_depth, ctx->io[0], n_leaves,
-                          root, insert_depth, root_depth, has_root, ctx->stream, leaves);
+                          root, insert_depth, root_depth, has_root, ctx->stream, &feed);
 }
 
 int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels,
@@ -927,38 +1043,11 @@ int inf_tree_build(inf_ctx* ctx, uint32_t arity, uint32_t depth, int prepend_bla
     if (n_total == 0) return INF_ERR_MERGE_FAILED;             // nothing to build a tree over
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    inf_tree* t = new inf_tree();
-    t->ctx = ctx; t->arity = arity; t->depth = depth; t->shift = shift; t->n_leaves = n_leaves;
-    uint64_t total_nodes = 0, c = n_total;
-    for (uint32_t l = 0; l <= depth; l++) {
-        t->offsets.push_back(total_nodes);
-        t->counts.push_back(c);
-        total_nodes += c;
-        c = (c + arity - 1) / arity;
-    }
-    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
-    cudaStream_t st = ctx->stream;
-    auto fail = [&](int rc) { inf_tree_destroy(t); return rc; };
-    cudaError_t e;
-    if ((e = cudaMalloc(&t->d_nodes, total_nodes * 32)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc tree levels"));
-    if ((e = cudaMalloc(&t->d_level_ptrs, (depth + 1) * sizeof(void*))) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
-    if ((e = cudaMalloc(&t->d_level_counts, (depth + 1) * 8)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
-    if ((e = cudaMalloc(&t->d_zero_nodes, 33 * 32)) != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc"));
-    std::vector<void*> ptrs;
-    for (uint32_t l = 0; l <= depth; l++) ptrs.push_back((char*)t->d_nodes + t->offsets[l] * 32);
-    // level 0 = [blank leaf] ++ leaves, materialised so that paths index one array
-    if (shift) e = cudaMemcpyAsync(t->d_nodes, Z[0], 32, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && n_leaves)
-        e = cudaMemcpyAsync((char*)t->d_nodes + shift * 32, leaves, n_leaves * 32, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_level_ptrs, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_level_counts, t->counts.data(), t->counts.size() * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t->d_zero_nodes, Z, 33 * 32, cudaMemcpyHostToDevice, st);
-    for (uint32_t l = 0; l < depth && e == cudaSuccess; l++)
-        e = launch_level(arity, ptrs[l], 0, t->counts[l], ptrs[l + 1], t->counts[l + 1], Z[l], st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "inf_tree_build"));
-    *out = t;
-    return INF_OK;
+    const LeafFeed feed = host_leaf_feed(ctx, leaves);
+    int has = 0;
+    int rc = tree_merge_dev(ctx, arity, depth, prepend_blank_leaf, 1, nullptr, n_leaves, nullptr, nullptr, nullptr, &has,
+                            ctx->stream, &feed, out);
+    return rc == INF_ERR_TREE_ALREADY_MERGED ? INF_OK : rc;    // exactly arity^depth leaves is a full tree, not an error
 }
 
 int inf_tree_root(inf_tree* tree, uint8_t root[32]) {
@@ -971,25 +1060,52 @@ int inf_tree_root(inf_tree* tree, uint8_t root[32]) {
 }
 
 int inf_tree_paths(inf_tree* tree, const uint64_t* leaf_indices, uint64_t n_idx, uint8_t* paths) {
+    return inf_tree_node_paths(tree, 0, leaf_indices, n_idx, paths);
+}
+
+int inf_tree_node_paths(inf_tree* tree, uint32_t level, const uint64_t* node_indices, uint64_t n_idx, uint8_t* paths) {
     if (!tree) return INF_ERR_NULL_POINTER;
-    if (n_idx && (!leaf_indices || !paths)) return INF_ERR_NULL_POINTER;
-    if (n_idx == 0 || tree->depth == 0) return INF_OK;
+    if (level > tree->depth) return INF_ERR_BAD_DEPTH;
+    if (n_idx && (!node_indices || !paths)) return INF_ERR_NULL_POINTER;
+    const uint32_t levels_up = tree->depth - level;
+    if (n_idx == 0 || levels_up == 0) return INF_OK;
     inf_ctx* ctx = tree->ctx;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    const uint64_t cap = pow_sat(tree->arity, tree->depth);
+    const uint64_t cap = pow_sat(tree->arity, levels_up);
     for (uint64_t i = 0; i < n_idx; i++)
-        if (leaf_indices[i] >= cap) return INF_ERR_BAD_DEPTH;
-    const size_t out_bytes = (size_t)n_idx * tree->depth * (tree->arity - 1) * 32;
+        if (node_indices[i] >= cap) return INF_ERR_BAD_DEPTH;
+    const size_t out_bytes = (size_t)n_idx * levels_up * (tree->arity - 1) * 32;
     int rc;
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_idx * 8))) return rc;
     if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], out_bytes))) return rc;
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(ctx->io[0], leaf_indices, n_idx * 8, cudaMemcpyHostToDevice, st));
-    CU(launch_gather_paths((const void* const*)tree->d_level_ptrs, (const uint64_t*)tree->d_level_counts,
-                           tree->d_zero_nodes, tree->arity, tree->depth, ctx->io[0], n_idx, ctx->io[1], st));
+    CU(cudaMemcpyAsync(ctx->io[0], node_indices, n_idx * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_gather_paths((const void* const*)tree->d_level_ptrs + level, (const uint64_t*)tree->d_level_counts + level,
+                           (const char*)tree->d_zero_nodes + (size_t)level * 32, tree->arity, levels_up, ctx->io[0], n_idx,
+                           ctx->io[1], st));
     CU(cudaMemcpyAsync(paths, ctx->io[1], out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return INF_OK;
+}
+
+int inf_tree_level_nodes(inf_tree* tree, uint32_t level, uint64_t first, uint64_t count, uint8_t* out) {
+    if (!tree) return INF_ERR_NULL_POINTER;
+    if (level > tree->depth) return INF_ERR_BAD_DEPTH;
+    if (count && !out) return INF_ERR_NULL_POINTER;
+    if (count == 0) return INF_OK;
+    inf_ctx* ctx = tree->ctx;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    const uint64_t cap = pow_sat(tree->arity, tree->depth - level), have = tree->counts[level];
+    if (first > cap || count > cap - first) return INF_ERR_BAD_DEPTH;
+    // stored nodes first, then the level's zero value for the all-zero subtrees to their right
+    const uint64_t n_real = first < have ? std::min<uint64_t>(count, have - first) : 0;
+    if (n_real)
+        CU(cudaMemcpy(out, (const char*)tree->d_nodes + (tree->offsets[level] + first) * 32, (size_t)n_real * 32,
+                      cudaMemcpyDeviceToHost));
+    const uint8_t* z = ctx->zeroes[tree->arity == 2 ? 0 : 1][level];
+    for (uint64_t i = n_real; i < count; i++) memcpy(out + 32 * i, z, 32);
     return INF_OK;
 }
 
@@ -1031,6 +1147,83 @@ int inf_merkle_roots_from_paths(inf_ctx* ctx, uint32_t arity, uint32_t depth, co
                   : launch_path_root_t6(d_idx, d_leaves, d_paths, depth, ctx->io[1], n, st));
     CU(cudaMemcpyAsync(roots, ctx->io[1], n * 32, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return INF_OK;
+}
+
+// ---- replay from raw inputs: leaf hashing chained into the tree on the device ------------------
+int inf_replay_registrations(inf_ctx* ctx, uint32_t registration_depth, const uint8_t* public_keys,
+                             const uint64_t* timestamps, uint64_t n, uint8_t root[32],
+                             uint8_t process_commitment[32], uint32_t* insert_depth, uint8_t* leaves_out,
+                             inf_tree** retained) {
+    if (!ctx || !root || !process_commitment) return INF_ERR_NULL_POINTER;
+    if (n && (!public_keys || !timestamps)) return INF_ERR_NULL_POINTER;
+    if (retained) *retained = nullptr;
+    if (registration_depth > 32) return INF_ERR_BAD_DEPTH;
+    if (n + 1 > pow_sat(2, registration_depth)) return INF_ERR_TREE_ALREADY_FULL;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    const uint64_t chunk_out = 1ull << 18;
+    int rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * (size_t)std::min<uint64_t>(chunk_out * 2, n + 2) * 72 + 256))) return rc;
+    if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;
+    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, (const uint8_t*)timestamps, 8, 2, chunk_out,
+                                  [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
+                                      return launch_registration_leaves(a, b, o, c, st);
+                                  });
+    feed.leaves_out = leaves_out;
+    int has = 0;
+    uint32_t rdepth = 0;
+    // register_participant x n (provider.rs:218-241), then merge_registrations (provider.rs:289-311)
+    rc = tree_merge_dev(ctx, 2, registration_depth, 1, 0, ctx->io[1], n, root, insert_depth, &rdepth, &has, ctx->stream, &feed,
+                        retained);
+    if (rc) {
+        if (retained && *retained) { inf_tree_destroy(*retained); *retained = nullptr; }
+        return rc;
+    }
+    if (!has) return INF_ERR_MERGE_FAILED;
+    uint8_t in[3 * 32];
+    memcpy(in, root, 32);
+    memcpy(in + 32, host::EMPTY_BALLOT_ROOTS_BE[1], 32);
+    memset(in + 64, 0, 32);
+    rc = inf_poseidon_hash_batch(ctx, 3, 0, nullptr, in, 1, process_commitment);
+    return rc ? INF_ERR_HASH_FAILED : INF_OK;
+}
+
+int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8_t* public_keys,
+                            const uint8_t* data, uint64_t n, uint32_t registrations_count,
+                            uint32_t process_subtree_depth, uint32_t tally_subtree_depth, uint8_t root[32],
+                            int* has_root, uint32_t* insert_depth, uint32_t* expected_process,
+                            uint32_t* expected_tally, uint8_t* leaves_out, inf_tree** retained) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (n && (!public_keys || !data)) return INF_ERR_NULL_POINTER;
+    if (retained) *retained = nullptr;
+    if (has_root) *has_root = 0;
+    if (interaction_depth > 32) return INF_ERR_BAD_DEPTH;
+    if (n > pow_sat(5, interaction_depth)) return INF_ERR_TREE_ALREADY_FULL;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    const uint64_t chunk_out = 1ull << 15;
+    int rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * (size_t)std::min<uint64_t>(chunk_out * 5, n + 5) * 384 + 256))) return rc;
+    if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;
+    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, data, 320, 5, chunk_out,
+                                  [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
+                                      return launch_interaction_leaves(a, b, o, c, st);
+                                  });
+    feed.leaves_out = leaves_out;
+    uint32_t rdepth = 0;
+    // consume_interaction x n (provider.rs:243-287), then merge_interactions (provider.rs:313-327)
+    rc = tree_merge_dev(ctx, 5, interaction_depth, 0, 1, ctx->io[1], n, root, insert_depth, &rdepth, has_root, ctx->stream,
+                        &feed, retained);
+    if (rc) {
+        if (retained && *retained) { inf_tree_destroy(*retained); *retained = nullptr; }
+        return rc;
+    }
+    const uint32_t count = (uint32_t)n;
+    const uint32_t pb = (uint32_t)pow_sat(5, process_subtree_depth);
+    const uint32_t tb = (uint32_t)pow_sat(2, tally_subtree_depth);
+    if (expected_process) *expected_process = pb ? count / pb + ((count % pb) ? 1u : 0u) : 0u;
+    if (expected_tally) *expected_tally = tb ? 1u + registrations_count / tb : 0u;
     return INF_OK;
 }
 

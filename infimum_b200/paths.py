@@ -35,6 +35,30 @@ class RetainedTree:
                                                    a.ctypes.data if a.size else None, a.shape[0], C.byref(h)))
         self.handle = h
 
+    @classmethod
+    def _adopt(cls, handle, arity: int, depth: int, n_leaves: int, shift: int, ctx: Context) -> "RetainedTree":
+        """Wrap an inf_tree the library handed out (inf_replay_*)."""
+        t = cls.__new__(cls)
+        t.ctx, t.arity, t.depth, t.n_leaves, t.shift, t.handle = ctx, int(arity), int(depth), int(n_leaves), int(shift), handle
+        return t
+
+    def node_paths(self, level: int, node_indices) -> np.ndarray:
+        """(n, depth - level, arity-1, 32) sibling paths from nodes of `level` to the
+        root — with level = process_subtree_depth, the msgSubrootPathElements of
+        every batch (circuits/process-messages.circom:57,85) in one call."""
+        idx = np.ascontiguousarray(np.asarray(node_indices, dtype=np.uint64).reshape(-1))
+        out = np.empty((idx.size, self.depth - level, self.arity - 1, 32), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.inf_tree_node_paths(self.handle, level, idx.ctypes.data, idx.size, out.ctypes.data))
+        return out
+
+    def level_nodes(self, level: int, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """(count, 32) nodes of `level` starting at `first` (zero subtrees included)."""
+        if count is None:
+            count = max(-(-(self.n_leaves + self.shift) // self.arity ** level) - first, 0)
+        out = np.empty((count, 32), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.inf_tree_level_nodes(self.handle, level, first, count, out.ctypes.data))
+        return out
+
     @property
     def root(self) -> bytes:
         buf = C.create_string_buffer(32)

@@ -21,7 +21,7 @@ import numpy as np
 
 from .context import Context, get_context
 from .errors import MerkleTreeError
-from .leaves import interaction_leaves, registration_leaves
+from .leaves import interaction_leaves, registration_leaves, replay_interactions, replay_registrations
 from .tree import (PollStateTree, merge_interactions as _merge_interactions,
                    merge_registrations as _merge_registrations, new_interaction_tree, new_registration_tree)
 
@@ -94,13 +94,33 @@ class Poll:
             self._msg_pk, self._msg_data = [], []
             self.interactions.extend(lv)
 
+    def _untouched(self, tree: PollStateTree) -> bool:
+        """Nothing hashed in yet: the whole poll can be replayed raw rows -> root on the device."""
+        return tree.root is None and tree._fresh and tree._pending == 0
+
     def merge_registrations(self) -> "Poll":
+        if self._reg_pk and self._untouched(self.registrations):
+            pk, ts = np.frombuffer(b"".join(self._reg_pk), dtype=np.uint8), np.array(self._reg_ts, dtype=np.uint64)
+            self.registrations, c, _, _ = replay_registrations(self.config.registration_depth, pk, ts, self.ctx)
+            self._reg_pk, self._reg_ts = [], []
+            self.commitment.process = (0, c)
+            return self
         self._flush()
         self.registrations, c = _merge_registrations(self.registrations)
         self.commitment.process = (0, c)
         return self
 
     def merge_interactions(self) -> "Poll":
+        if self._msg_pk and self._untouched(self.interactions):
+            pk = np.frombuffer(b"".join(self._msg_pk), dtype=np.uint8)
+            data = np.frombuffer(b"".join(self._msg_data), dtype=np.uint8)
+            self._msg_pk, self._msg_data = [], []
+            self._flush()                                       # registrations still pending are hashed the usual way
+            self.interactions, ep, et, _, _ = replay_interactions(
+                self.config.interaction_depth, pk, data, self.registrations.count, self.config.process_subtree_depth,
+                self.config.tally_subtree_depth, self.ctx)
+            self.commitment.expected_process, self.commitment.expected_tally = ep, et
+            return self
         self._flush()
         self.interactions, ep, et = _merge_interactions(self.interactions, self.registrations.count,
                                                         self.config.process_subtree_depth,

@@ -199,6 +199,32 @@ class FakeLib:
             _set(rdepth, d)
         return OK
 
+    def inf_replay_registrations(self, ctx, depth, pk, ts, n, root, commitment, idepth, leaves_out, retained):
+        if n + 1 > 2 ** depth:
+            return FULL
+        lv = c_oracle.registration_leaves(np.frombuffer(_rd(pk, n * 64), dtype=np.uint8),
+                                          np.frombuffer(_rd(ts, n * 8), dtype=np.uint64)) if n else np.empty((0, 32), np.uint8)
+        if leaves_out is not None:
+            _wr(leaves_out, lv.tobytes())
+        rc, r, d, _ = c_oracle.tree_insert_merge(2, depth, True, False, lv)
+        _wr(root, r), _set(idepth, d)
+        _wr(commitment, c_oracle.hash_one([r, O.EMPTY_BALLOT_ROOTS[1].to_bytes(32, "big"), bytes(32)]))
+        return rc
+
+    def inf_replay_interactions(self, ctx, depth, pk, data, n, regs, psd, tsd, root, has, idepth, ep, et, leaves_out, retained):
+        _set(has, 0)
+        if n > 5 ** depth:
+            return FULL
+        lv = c_oracle.interaction_leaves(np.frombuffer(_rd(pk, n * 64), dtype=np.uint8),
+                                         np.frombuffer(_rd(data, n * 320), dtype=np.uint8)) if n else np.empty((0, 32), np.uint8)
+        if leaves_out is not None:
+            _wr(leaves_out, lv.tobytes())
+        rc, r, d, _ = c_oracle.tree_insert_merge(5, depth, False, True, lv)
+        if r is not None:
+            _wr(root, r), _set(has, 1)
+        _set(idepth, d), _set(ep, n // 5 ** psd + (1 if n % 5 ** psd else 0)), _set(et, 1 + regs // 2 ** tsd)
+        return rc
+
     # ---- leaves -------------------------------------------------------------------------
     def inf_registration_leaves(self, ctx, pk, ts, n, out):
         keys = _rd(pk, 64 * n)

@@ -392,10 +392,10 @@ def test_insert_and_merge_on_a_stored_frontier(ib, arity, full_depth, blank):
     after k inserts, append the rest in one batch, and get the oracle's incremental
     state — frontier, depth, count — then merge from that frontier, both ways."""
     import copy
-    allv = random_fr_bytes(900, seed=arity + 70)
+    allv = random_fr_bytes(640, seed=arity + 70)
     rng = random.Random(arity * 100 + full_depth)
-    for n in [0, 1, 2, 5, 24, 25, 26, 124, 125, 126, 255, 256, 257, 624, 625, 626, 700, 900]:
-        splits = sorted({0, n, n // 2, rng.randrange(n + 1), rng.randrange(n + 1)})
+    for n in [0, 1, 2, 5, 24, 25, 26, 124, 125, 126, 255, 256, 257, 626, 640]:
+        splits = sorted({0, n, rng.randrange(n + 1), rng.randrange(n + 1)})
         o = O.PollStateTree.new(arity, full_depth, (0, O.merkle_zeroes(arity)[0]) if blank else None)
         states = {}
         for i in range(n + 1):
@@ -526,6 +526,74 @@ def test_leaf_hashing_batches_vs_oracle(ib):
     got = ib.registration_leaves(pk, ts)
     idx = np.r_[0:50, (1 << 17) - 25:(1 << 17) + 77]
     assert (got[idx] == c_oracle.registration_leaves(pk[idx], ts[idx])).all()
+
+
+# ---- replay: raw rows -> leaves -> merged tree on the device (provider.rs:218-327) ---------------------
+@pytest.mark.parametrize("n", [0, 1, 4, 26, 700, 20000, (1 << 17) + 77])
+def test_replay_interactions_equals_leaf_hash_then_insert_merge(ib, n):
+    depth, psd = 8, 2
+    pk = random_fr_bytes(2 * max(n, 1), seed=71 + n, canonical=False).reshape(-1, 64)[:n]
+    data = random_fr_bytes(10 * max(n, 1), seed=72 + n, canonical=False).reshape(-1, 320)[:n]
+    t, ep, et, leaves, kept = ib.replay_interactions(depth, pk, data, 1000, psd, 1, want_leaves=True, retain=True)
+    exp_leaves = c_oracle.interaction_leaves(pk, data) if n else np.empty((0, 32), dtype=np.uint8)
+    assert (leaves == exp_leaves).all()
+    rc, root, d, count = c_oracle.tree_insert_merge(5, depth, False, True, exp_leaves)
+    assert rc == 0 and (t.root, t.depth, t.count, t.hashes) == (root, d, n, [])
+    assert (ep, et) == (-(-n // 25), 1 + 1000 // 2)
+    if n == 0:
+        assert kept is None and t.root is None
+        return
+    # the retained levels: every batch subroot and its path to the root, all batches in one call
+    assert kept.root == root
+    n_batches = -(-n // 5 ** psd)
+    sub = kept.level_nodes(psd)
+    assert sub.shape[0] == n_batches
+    zero = np.frombuffer(ib.get_merkle_zeroes(5)[0], dtype=np.uint8)
+    for b in {0, n_batches - 1, n_batches // 2}:
+        chunk = exp_leaves[b * 25:(b + 1) * 25]
+        assert sub[b].tobytes() == c_oracle.dense_tree_root(5, psd, chunk)
+    idx = np.unique(np.r_[0, n_batches - 1, np.random.default_rng(n).integers(0, n_batches, size=50)]).astype(np.uint64)
+    paths = kept.node_paths(psd, idx)
+    roots = ib.merkle_roots_from_paths(5, depth - psd, idx, sub[idx.astype(np.int64)], paths)
+    assert all(roots[k].tobytes() == root for k in range(len(idx)))
+    # a batch of all-zero leaves to the right of the stored nodes reads as zeroes[psd]
+    if n_batches < 5 ** (depth - psd):
+        assert kept.level_nodes(psd, n_batches, 1)[0].tobytes() == ib.get_merkle_zeroes(5)[psd]
+    kept.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 700, (1 << 19) + 5])
+def test_replay_registrations_equals_leaf_hash_then_insert_merge(ib, n):
+    depth = 21
+    pk = random_fr_bytes(2 * max(n, 1), seed=81 + n, canonical=False).reshape(-1, 64)[:n]
+    ts = np.random.default_rng(82 + n).integers(0, 2 ** 63, size=n, dtype=np.uint64)
+    t, commitment, leaves, kept = ib.replay_registrations(depth, pk, ts, want_leaves=True, retain=True)
+    exp_leaves = c_oracle.registration_leaves(pk, ts) if n else np.empty((0, 32), dtype=np.uint8)
+    assert (leaves == exp_leaves).all()
+    rc, root, d, count = c_oracle.tree_insert_merge(2, depth, True, False, exp_leaves)
+    assert rc == 0 and (t.root, t.depth, t.count, t.hashes) == (root, d, n, [])
+    assert commitment == c_oracle.hash_one([root, ib.empty_ballot_roots()[1], bytes(32)])
+    assert kept.root == root
+    if n:
+        idx = np.unique(np.r_[0, 1, n, np.random.default_rng(n).integers(0, n + 1, size=30)]).astype(np.uint64)
+        logical = np.concatenate([np.frombuffer(ib.get_merkle_zeroes(2)[0], dtype=np.uint8).reshape(1, 32), exp_leaves])
+        roots = ib.merkle_roots_from_paths(2, kept.depth, idx, logical[idx.astype(np.int64)], kept.paths(idx))
+        assert all(roots[k].tobytes() == root for k in range(len(idx)))
+    kept.close()
+
+
+def test_replay_capacity_errors(ib):
+    pk = random_fr_bytes(2 * 26, seed=91).reshape(-1, 64)
+    data = random_fr_bytes(10 * 26, seed=92).reshape(-1, 320)
+    with pytest.raises(ib.MerkleTreeError) as e:
+        ib.replay_interactions(2, pk, data, 0, 1, 1)             # 26 messages, capacity 25
+    assert e.value.code == 1
+    t, _, _, _, _ = ib.replay_interactions(2, pk[:25], data[:25], 0, 1, 1)     # exactly full: completed by insert
+    rc, root, d, _ = c_oracle.tree_insert_merge(5, 2, False, True, c_oracle.interaction_leaves(pk[:25], data[:25]))
+    assert rc == 2 and t.root == root and t.depth == d
+    with pytest.raises(ib.MerkleTreeError) as e:
+        ib.replay_registrations(2, pk[:4], np.arange(4, dtype=np.uint64))      # blank + 4 > 4
+    assert e.value.code == 1
 
 
 # ---- Merkle paths and verify_outcome (provider.rs:76-139, 396-436) ---------------------------------

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "fr_lat.cuh"
 #include "poseidon.cuh"
+#include "fr29.cuh"
 using namespace inf;
 
 template <int K>
@@ -53,6 +54,32 @@ __global__ void __launch_bounds__(128) k_acc(unsigned long long* out, unsigned b
 #pragma unroll
     for (int k = 0; k < K; k++) x ^= acc[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// the 29-bit-limb, carry-free representation (tools/experiments/fr29.cuh): lone-warp latency
+template <int OP>
+__global__ void __launch_bounds__(128) k_prim29(uint32_t* out, const uint32_t* in, long long* cyc) {
+    uint32_t x[3][NL], y[3][NL];
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < NL; i++) { x[j][i] = (in[i] + threadIdx.x + j) & LMASK; y[j][i] = in[8 + i + j] & LMASK; }
+    for (int j = 0; j < 3; j++) { x[j][NL - 1] &= 0xfffff; y[j][NL - 1] &= 0xfffff; }
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 1000; it++) {
+        uint32_t t[NL];
+        if (OP == 0) mul29(t, x[0], y[0]);
+        if (OP == 1) sqr29(t, x[0]);
+        if (OP == 2) { uint32_t x2[NL], x4[NL]; sqr29(x2, x[0]); sqr29(x4, x2); mul29(t, x4, x[0]); }
+        if (OP == 3) dot29<3, NL>(t, &x[0][0], &y[0][0], y[1], nullptr);
+        if (OP == 4) { uint32_t x2[NL], x4[NL]; sqr29(x2, x[0]); sqr29(x4, x2); dot29<1, NL>(t, x4, x[0], nullptr, x[1]); }
+        for (int i = 0; i < NL; i++) x[0][i] = t[i];
+        x[0][NL - 1] &= 0xfffff;
+    }
+    long long t1 = clock64();
+    uint32_t acc = 0;
+    for (int i = 0; i < NL; i++) acc ^= x[0][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
@@ -126,6 +153,13 @@ int main() {
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);                                \
     printf("lone warp, dependent %s: %.0f cycles\n", names[OP], c / 1000.0);
     PR(0) PR(1) PR(2) PR(3) PR(4) PR(5) PR(6) PR(7) PR(8) PR(9) PR(10) PR(11) PR(12) PR(13)
+    const char* names29[] = {"mul29", "sqr29", "sbox29 (sqr, sqr, mul)", "dot29<3>", "sbox29 + addend (one partial round of the chain)"};
+#define PR29(OP)                                                                   \
+    for (int rep = 0; rep < 2; rep++) k_prim29<OP><<<148, 128>>>(out, in, cyc);    \
+    cudaDeviceSynchronize();                                                       \
+    cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);                                \
+    printf("lone warp, dependent %s: %.0f cycles\n", names29[OP], c / 1000.0);
+    PR29(0) PR29(1) PR29(2) PR29(3) PR29(4)
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
