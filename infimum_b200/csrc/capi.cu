@@ -191,6 +191,62 @@ LeafFeed host_leaf_feed(inf_ctx* ctx, const uint8_t* h_leaves) {
     return f;
 }
 
+// Levels level_in .. level_in + n_levels - 1 over a run of nodes (`shift` leading zero nodes, then
+// n_in nodes at d_in): output of local level l goes to dst_of(l).  With a feed, level 0's input is
+// produced chunk by chunk on the pipeline streams (see LeafFeed) and `st` is made to wait for them.
+// Everything is enqueued; nothing is synchronised.  n_levels >= 1.
+int reduce_levels(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_levels, uint64_t shift,
+                  const void* d_in, uint64_t n_in, const LeafFeed* feed,
+                  const std::function<char*(uint32_t)>& dst_of, cudaStream_t st, const void** out_ptr,
+                  uint64_t* out_n) {
+    const uint8_t(*Z)[32] = ctx->zeroes[arity == 2 ? 0 : 1];
+    const uint64_t n_total = n_in + shift;
+    const uint64_t n1 = (n_total + arity - 1) / arity;
+    const void* cur = d_in;
+    uint64_t n_cur = n_in, sh = shift;
+    uint32_t l_first = 0;
+    int rc;
+    if (feed) {
+        const uint64_t chunk_out = feed->chunk_out;
+        int k = 0;
+        for (uint64_t o0 = 0; o0 < n1; o0 += chunk_out, k++) {
+            const uint64_t o1 = std::min<uint64_t>(o0 + chunk_out, n1);
+            const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
+            const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
+            cudaStream_t ps = ctx->pipe[k % 3];
+            char* dl = (char*)d_in + leaf_lo * 32;
+            if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return rc;
+            CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, dst_of(0) + o0 * 32, o1 - o0,
+                            Z[level_in], ps));
+        }
+        for (int i = 0; i < 3; i++) {
+            CU(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
+            CU(cudaStreamWaitEvent(st, ctx->pipe_done[i], 0));
+        }
+        if (feed->leaves_out && n_in) {
+            // all leaves exist once every pipeline stream is through: read them back on pipe[0]
+            // while `st` hashes the upper levels (the caller synchronises pipe[0])
+            for (int i = 1; i < 3; i++) CU(cudaStreamWaitEvent(ctx->pipe[0], ctx->pipe_done[i], 0));
+            CU(cudaMemcpyAsync(feed->leaves_out, d_in, (size_t)n_in * 32, cudaMemcpyDeviceToHost, ctx->pipe[0]));
+        }
+        cur = dst_of(0);
+        n_cur = n1;
+        sh = 0;
+        l_first = 1;
+    }
+    for (uint32_t l = l_first; l < n_levels; l++) {
+        const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
+        void* dst = dst_of(l);
+        CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[level_in + l], st));
+        cur = dst;
+        n_cur = n_next;
+        sh = 0;
+    }
+    if (out_ptr) *out_ptr = cur;
+    if (out_n) *out_n = n_cur;
+    return INF_OK;
+}
+
 // Core of the tree merge.  Leaves the root (if any) in host memory.  `st` is synchronised
 // before return.  Without a feed the leaves are already at d_leaves; with one, d_leaves is the
 // (uninitialised) device area they are produced into.  With `keep`, every level is retained in
@@ -253,7 +309,7 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
         return code;
     };
     // output of level l (the nodes of level l + 1)
-    auto level_dst = [&](uint32_t l) -> char* {
+    const std::function<char*(uint32_t)> level_dst = [&](uint32_t l) -> char* {
         return kt ? (char*)kt->d_nodes + kt->offsets[l + 1] * 32 : (char*)ctx->scratch[l & 1];
     };
     uint8_t root_local[32];
@@ -276,45 +332,9 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
             if ((rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
             if ((rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
         }
-        const void* cur = d_leaves;
-        uint64_t n_cur = n_leaves, sh = shift;
-        uint32_t l_first = 0;
-        if (feed) {
-            const uint64_t chunk_out = feed->chunk_out;
-            int k = 0;
-            for (uint64_t o0 = 0; o0 < n1; o0 += chunk_out, k++) {
-                const uint64_t o1 = std::min<uint64_t>(o0 + chunk_out, n1);
-                const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
-                const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
-                cudaStream_t ps = ctx->pipe[k % 3];
-                char* dl = (char*)d_leaves + leaf_lo * 32;
-                if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return bail(rc);
-                CUB(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, level_dst(0) + o0 * 32, o1 - o0,
-                                 Z[0], ps));
-            }
-            for (int i = 0; i < 3; i++) {
-                CUB(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
-                CUB(cudaStreamWaitEvent(st, ctx->pipe_done[i], 0));
-            }
-            if (feed->leaves_out && n_leaves) {
-                // all leaves exist once every pipeline stream is through: read them back on pipe[0]
-                // while `st` hashes the upper levels
-                for (int i = 1; i < 3; i++) CUB(cudaStreamWaitEvent(ctx->pipe[0], ctx->pipe_done[i], 0));
-                CUB(cudaMemcpyAsync(feed->leaves_out, d_leaves, (size_t)n_leaves * 32, cudaMemcpyDeviceToHost, ctx->pipe[0]));
-            }
-            cur = level_dst(0);
-            n_cur = n1;
-            sh = 0;
-            l_first = 1;
-        }
-        for (uint32_t l = l_first; l < rdepth; l++) {
-            const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
-            void* dst = level_dst(l);
-            CUB(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[l], st));
-            cur = dst;
-            n_cur = n_next;
-            sh = 0;
-        }
+        const void* cur = nullptr;
+        if ((rc = reduce_levels(ctx, arity, 0, rdepth, shift, d_leaves, n_leaves, feed, level_dst, st, &cur, nullptr)))
+            return bail(rc);
         CUB(cudaMemcpyAsync(root_local, cur, 32, cudaMemcpyDeviceToHost, st));
         CUB(cudaStreamSynchronize(st));
         if (feed && feed->leaves_out) CUB(cudaStreamSynchronize(ctx->pipe[0]));
@@ -495,11 +515,10 @@ int tree_append_core(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const ui
 
 // rows [lo, hi) of two host arrays -> per-stream staging -> leaf kernel -> dst
 template <class Launch>
-LeafFeed raw_rows_feed(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* in1, size_t row1, uint32_t arity,
-                       uint64_t chunk_out, Launch launch) {
+LeafFeed raw_rows_feed(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* in1, size_t row1,
+                       uint64_t chunk_out, size_t slot_rows, Launch launch) {
     LeafFeed f;
     f.chunk_out = chunk_out;
-    const size_t slot_rows = (size_t)chunk_out * arity;
     f.fill = [=](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot) -> int {
         char* s0 = (char*)ctx->io[0] + (size_t)slot * slot_rows * (row0 + row1);
         char* s1 = s0 + slot_rows * row0;
@@ -920,17 +939,12 @@ int inf_tree_reduce_dev(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_
     int rc;
     if (n_levels > 1 && (rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
     if (n_levels > 2 && (rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
-    const void* cur = d_in;
-    uint64_t n_cur = n_in, sh = shift;
-    for (uint32_t l = 0; l < n_levels; l++) {
-        const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
-        void* dst = (l + 1 == n_levels) ? d_out : ctx->scratch[l & 1];
-        CU(launch_level(arity, cur, sh, n_cur, dst, n_next, Z[level_in + l], st));
-        cur = dst;
-        n_cur = n_next;
-        sh = 0;
-    }
-    if (n_out) *n_out = n_cur;
+    const std::function<char*(uint32_t)> dst_of = [&](uint32_t l) -> char* {
+        return (char*)((l + 1 == n_levels) ? d_out : ctx->scratch[l & 1]);
+    };
+    uint64_t n_res = 0;
+    if ((rc = reduce_levels(ctx, arity, level_in, n_levels, shift, d_in, n_in, nullptr, dst_of, st, nullptr, &n_res))) return rc;
+    if (n_out) *n_out = n_res;
     return INF_OK;
 }
 
@@ -1163,10 +1177,11 @@ int inf_replay_registrations(inf_ctx* ctx, uint32_t registration_depth, const ui
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     const uint64_t chunk_out = 1ull << 18;
+    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out * 2, n + 2) + 3) & ~(size_t)3;   // rows one pipeline stream stages at a time (keeps the slots 16-byte aligned)
     int rc;
-    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * (size_t)std::min<uint64_t>(chunk_out * 2, n + 2) * 72 + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 72))) return rc;
     if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;
-    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, (const uint8_t*)timestamps, 8, 2, chunk_out,
+    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, (const uint8_t*)timestamps, 8, chunk_out, slot_rows,
                                   [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
                                       return launch_registration_leaves(a, b, o, c, st);
                                   });
@@ -1203,10 +1218,11 @@ int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     const uint64_t chunk_out = 1ull << 15;
+    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out * 5, n + 5) + 3) & ~(size_t)3;
     int rc;
-    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * (size_t)std::min<uint64_t>(chunk_out * 5, n + 5) * 384 + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 384))) return rc;
     if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;
-    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, data, 320, 5, chunk_out,
+    LeafFeed feed = raw_rows_feed(ctx, public_keys, 64, data, 320, chunk_out, slot_rows,
                                   [](const void* a, const void* b, void* o, uint64_t c, cudaStream_t st) {
                                       return launch_interaction_leaves(a, b, o, c, st);
                                   });
@@ -1271,6 +1287,44 @@ int inf_merge_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint8
 int inf_internal_stream(inf_ctx* ctx, void** stream) {
     if (!ctx || !stream) return INF_ERR_NULL_POINTER;
     *stream = (void*)ctx->stream;
+    return INF_OK;
+}
+// Reduce a run of level-0 nodes that is still in host memory by n_levels (>= 1) levels into d_out:
+// chunked upload overlapped with level-0 hashing on the context's pipeline streams, the rest on its
+// own stream.  Enqueues only; the caller synchronises the context's stream (inf_internal_drain).
+int inf_internal_tree_reduce_host(inf_ctx* ctx, uint32_t arity, uint32_t n_levels, uint64_t shift,
+                                  const uint8_t* h_in, uint64_t n_in, void* d_out, uint64_t* n_out) {
+    if (!ctx || !d_out || (n_in && !h_in)) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (n_levels < 1 || n_levels > 32) return INF_ERR_BAD_DEPTH;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    const uint64_t n_total = n_in + shift;
+    if (n_total == 0) {
+        if (n_out) *n_out = 0;
+        return INF_OK;
+    }
+    const uint64_t n1 = (n_total + arity - 1) / arity, n2 = (n1 + arity - 1) / arity;
+    int rc;
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], std::max<uint64_t>(n_in, 1) * 32))) return rc;
+    if (n_levels > 1 && (rc = grow(ctx, &ctx->scratch[0], &ctx->scratch_bytes[0], n1 * 32))) return rc;
+    if (n_levels > 2 && (rc = grow(ctx, &ctx->scratch[1], &ctx->scratch_bytes[1], n2 * 32))) return rc;
+    const LeafFeed feed = host_leaf_feed(ctx, h_in);
+    const std::function<char*(uint32_t)> dst_of = [&](uint32_t l) -> char* {
+        return (char*)((l + 1 == n_levels) ? d_out : ctx->scratch[l & 1]);
+    };
+    return reduce_levels(ctx, arity, 0, n_levels, shift, ctx->io[0], n_in, &feed, dst_of, ctx->stream, nullptr, n_out);
+}
+// Wait for everything queued on the context's streams (also after an error).
+int inf_internal_drain(inf_ctx* ctx) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    cudaError_t e = cudaSuccess, e2;
+    for (int i = 0; i < 3; i++)
+        if ((e2 = cudaStreamSynchronize(ctx->pipe[i])) != cudaSuccess) e = e2;
+    if ((e2 = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) e = e2;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "drain");
     return INF_OK;
 }
 int inf_internal_grow_io(inf_ctx* ctx, int which, size_t bytes, void** ptr) {

@@ -15,12 +15,17 @@
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 // internal entry points of capi.cu
 extern "C" int inf_internal_stream(inf_ctx* ctx, void** stream);
 extern "C" int inf_internal_grow_io(inf_ctx* ctx, int which, size_t bytes, void** ptr);
+extern "C" int inf_internal_tree_reduce_host(inf_ctx* ctx, uint32_t arity, uint32_t n_levels, uint64_t shift,
+                                             const uint8_t* h_in, uint64_t n_in, void* d_out, uint64_t* n_out);
+extern "C" int inf_internal_drain(inf_ctx* ctx);
 
 namespace {
 
@@ -34,8 +39,10 @@ struct Nccl {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::mutex mu;
     bool load() {
-        if (handle) return true;
+        std::lock_guard<std::mutex> lock(mu);       // inf_multi_init may be called from several threads
+        if (handle) return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd;
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
             handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (handle) break;
@@ -173,97 +180,135 @@ int inf_multi_tree_merge(inf_multi* m, uint32_t arity, uint32_t full_depth, int 
         s1[g] = n_sub * (g + 1) / G;
         width = std::max(width, s1[g] - s0[g]);
     }
+    uint8_t zeroes[33][32];
+    inf_merkle_zeroes(m->ctx[0], arity, &zeroes[0][0]);
     const size_t gather = (size_t)width * 32;
     cudaError_t e = cudaSuccess;
-    auto fail_cuda = [&](const char* what) {
-        m->last_error = std::string(what) + ": " + cudaGetErrorString(e);
-        return INF_ERR_CUDA;
+    // Every exit after work has been queued goes through here: nothing may still be reading the
+    // caller's leaves, or using the contexts' buffers, when the call returns.
+    auto finish = [&](int code, const char* what) {
+        for (int g = 0; g < G; g++) {
+            const int drc = inf_internal_drain(m->ctx[g]);
+            if (!code && drc) code = drc;
+        }
+        if (code == INF_ERR_CUDA && what) m->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        else if (code) m->last_error = inf_strerror(code);
+        return code;
     };
     if (gather > m->gather_bytes) {
+        // drop the old buffers first and forget them, so that a failed allocation leaves the object
+        // with no buffers and gather_bytes == 0 rather than with dangling pointers
+        m->gather_bytes = 0;
         for (int g = 0; g < G; g++) {
             cudaSetDevice(m->devices[g]);
             if (m->send[g]) cudaFree(m->send[g]);
             if (m->recv[g]) cudaFree(m->recv[g]);
-            if ((e = cudaMalloc(&m->send[g], gather)) != cudaSuccess) return fail_cuda("cudaMalloc");
-            if ((e = cudaMalloc(&m->recv[g], gather * G)) != cudaSuccess) return fail_cuda("cudaMalloc");
+            m->send[g] = m->recv[g] = nullptr;
+        }
+        for (int g = 0; g < G; g++) {
+            cudaSetDevice(m->devices[g]);
+            if ((e = cudaMalloc(&m->send[g], gather)) != cudaSuccess || (e = cudaMalloc(&m->recv[g], gather * G)) != cudaSuccess) {
+                for (int h = 0; h <= g; h++) {
+                    cudaSetDevice(m->devices[h]);
+                    if (m->send[h]) cudaFree(m->send[h]);
+                    if (m->recv[h]) cudaFree(m->recv[h]);
+                    m->send[h] = m->recv[h] = nullptr;
+                }
+                cudaGetLastError();
+                return finish(e == cudaErrorMemoryAllocation ? INF_ERR_OUT_OF_MEMORY : INF_ERR_CUDA, "cudaMalloc");
+            }
         }
         m->gather_bytes = gather;
     }
     std::vector<cudaStream_t> st(G);
-    // 1. per device: upload the slice, reduce to level k into the send buffer
     for (int g = 0; g < G; g++) {
-        cudaSetDevice(m->devices[g]);
         void* sp = nullptr;
         inf_internal_stream(m->ctx[g], &sp);
         st[g] = (cudaStream_t)sp;
+    }
+    // 1. per device, on a thread of its own: upload the slice in chunks, reduce it to level k into the send buffer
+    std::vector<int> rcs(G, INF_OK);
+    auto reduce_on = [&](int g) {
+        if (s1[g] == s0[g]) return;
+        cudaSetDevice(m->devices[g]);
         const uint64_t lo_log = s0[g] * w, hi_log = std::min<uint64_t>(s1[g] * w, n_total);
         const uint64_t lo = lo_log >= shift ? lo_log - shift : 0, hi = hi_log >= shift ? hi_log - shift : 0;
         const uint64_t cnt = hi > lo ? hi - lo : 0;
-        const uint64_t sh = (s0[g] == 0 && s1[g] > 0) ? shift : 0;
-        if (s1[g] == s0[g]) continue;
-        void* d_leaves = nullptr;
-        int rc = inf_internal_grow_io(m->ctx[g], 0, std::max<uint64_t>(cnt, 1) * 32, &d_leaves);
-        if (rc) return rc;
-        if (cnt && (e = cudaMemcpyAsync(d_leaves, leaves + lo * 32, cnt * 32, cudaMemcpyHostToDevice, st[g])) != cudaSuccess)
-            return fail_cuda("cudaMemcpyAsync H2D");
-        if ((e = cudaMemsetAsync(m->send[g], 0, gather, st[g])) != cudaSuccess) return fail_cuda("cudaMemsetAsync");
+        const uint64_t sh = s0[g] == 0 ? shift : 0;
+        if (cudaMemsetAsync(m->send[g], 0, gather, st[g]) != cudaSuccess) {
+            rcs[g] = INF_ERR_CUDA;
+            return;
+        }
         uint64_t got = 0;
-        rc = inf_tree_reduce_dev(m->ctx[g], arity, 0, k, sh, d_leaves, cnt, m->send[g], &got, st[g]);
-        if (rc) return rc;
-        if (got != s1[g] - s0[g]) return INF_ERR_MERGE_FAILED;
+        if (k == 0) {                                            // the run is the leaves themselves
+            // (only trees too small to be worth sharding: fewer than 64 x G leaves)
+            cudaError_t ce = cudaSuccess;
+            for (uint64_t i = 0; i < sh && ce == cudaSuccess; i++)
+                ce = cudaMemcpyAsync((char*)m->send[g] + 32 * i, zeroes[0], 32, cudaMemcpyHostToDevice, st[g]);
+            if (ce == cudaSuccess && cnt)
+                ce = cudaMemcpyAsync((char*)m->send[g] + 32 * sh, leaves + lo * 32, cnt * 32, cudaMemcpyHostToDevice, st[g]);
+            rcs[g] = ce == cudaSuccess ? INF_OK : INF_ERR_CUDA;
+            got = cnt + sh;
+        } else {
+            rcs[g] = inf_internal_tree_reduce_host(m->ctx[g], arity, k, sh, leaves + lo * 32, cnt, m->send[g], &got);
+        }
+        if (!rcs[g] && got != s1[g] - s0[g]) rcs[g] = INF_ERR_MERGE_FAILED;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; g++) th.emplace_back(reduce_on, g);
+        reduce_on(0);
+        for (auto& t : th) t.join();
     }
+    for (int g = 0; g < G; g++)
+        if (rcs[g]) return finish(rcs[g], "device reduction");
     // 2. exchange the subtree roots
     if (G > 1) {
         if (m->use_nccl) {
             g_nccl.GroupStart();
+            bool bad = false;
             for (int g = 0; g < G; g++) {
                 cudaSetDevice(m->devices[g]);
-                if (g_nccl.AllGather(m->send[g], m->recv[g], gather, /*ncclChar*/ 0, m->comms[g], st[g]) != 0) {
-                    g_nccl.GroupEnd();
-                    return INF_ERR_NCCL;
-                }
+                if (g_nccl.AllGather(m->send[g], m->recv[g], gather, /*ncclChar*/ 0, m->comms[g], st[g]) != 0) bad = true;
             }
-            if (g_nccl.GroupEnd() != 0) return INF_ERR_NCCL;
+            if (g_nccl.GroupEnd() != 0 || bad) return finish(INF_ERR_NCCL, nullptr);
         } else {
             // peer copies into device 0's receive buffer, ordered after each producer
             for (int g = 0; g < G; g++) {
                 cudaSetDevice(m->devices[g]);
-                if ((e = cudaStreamSynchronize(st[g])) != cudaSuccess) return fail_cuda("cudaStreamSynchronize");
+                if ((e = cudaStreamSynchronize(st[g])) != cudaSuccess) return finish(INF_ERR_CUDA, "cudaStreamSynchronize");
             }
             cudaSetDevice(m->devices[0]);
             for (int g = 0; g < G; g++)
                 if ((e = cudaMemcpyPeerAsync((char*)m->recv[0] + gather * g, m->devices[0], m->send[g], m->devices[g],
                                              gather, st[0])) != cudaSuccess)
-                    return fail_cuda("cudaMemcpyPeerAsync");
+                    return finish(INF_ERR_CUDA, "cudaMemcpyPeerAsync");
         }
     }
     // 3. device 0: compact the runs and finish the top levels
     cudaSetDevice(m->devices[0]);
     void* d_nodes = nullptr;
     int rc = inf_internal_grow_io(m->ctx[0], 1, std::max<uint64_t>(n_sub, 1) * 32 + 32, &d_nodes);
-    if (rc) return rc;
+    if (rc) return finish(rc, nullptr);
     uint64_t off = 0;
     for (int g = 0; g < G; g++) {
         const uint64_t c = s1[g] - s0[g];
         if (!c) continue;
         const void* src = G > 1 ? (const void*)((char*)m->recv[0] + gather * g) : (const void*)m->send[0];
         if ((e = cudaMemcpyAsync((char*)d_nodes + off * 32, src, c * 32, cudaMemcpyDeviceToDevice, st[0])) != cudaSuccess)
-            return fail_cuda("cudaMemcpyAsync D2D");
+            return finish(INF_ERR_CUDA, "cudaMemcpyAsync D2D");
         off += c;
     }
     void* d_root = (char*)d_nodes + n_sub * 32;
     uint64_t got = 0;
     rc = inf_tree_reduce_dev(m->ctx[0], arity, k, rdepth - k, 0, d_nodes, n_sub, d_root, &got, st[0]);
-    if (rc) return rc;
-    if (got != 1) return INF_ERR_MERGE_FAILED;
+    if (rc) return finish(rc, nullptr);
+    if (got != 1) return finish(INF_ERR_MERGE_FAILED, nullptr);
     uint8_t r[32];
-    if ((e = cudaMemcpyAsync(r, d_root, 32, cudaMemcpyDeviceToHost, st[0])) != cudaSuccess) return fail_cuda("D2H root");
-    if ((e = cudaStreamSynchronize(st[0])) != cudaSuccess) return fail_cuda("cudaStreamSynchronize");
-    // with NCCL every device took part in the collective on its own stream: drain them
-    for (int g = 1; g < G; g++) {
-        cudaSetDevice(m->devices[g]);
-        if ((e = cudaStreamSynchronize(st[g])) != cudaSuccess) return fail_cuda("cudaStreamSynchronize");
-    }
+    if ((e = cudaMemcpyAsync(r, d_root, 32, cudaMemcpyDeviceToHost, st[0])) != cudaSuccess) return finish(INF_ERR_CUDA, "D2H root");
+    // the root is there when device 0's stream is; with NCCL every device took part in the
+    // collective on its own stream: drain them all
+    if ((rc = finish(INF_OK, nullptr))) return rc;
     if (root) memcpy(root, r, 32);
     if (has_root) *has_root = 1;
     return completed ? INF_ERR_TREE_ALREADY_MERGED : INF_OK;

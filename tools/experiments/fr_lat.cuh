@@ -1,3 +1,14 @@
+// EXPERIMENT — NOT USED BY THE PRODUCT.  Kept with its benchmark
+// (tools/experiments/lonewarp.cu) because the measurement decided the design: on
+// B200 this split-accumulator form is 2.1 x SLOWER for a lone warp than fr.cuh's
+// interleaved pass (mont_mul 1729 vs 813 cycles, sbox 4610 vs 2079): with the
+// product rows free of the reduction, ptxas keeps so many carry chains in flight
+// that their carries no longer fit the seven predicate registers and are spilled
+// to general registers (P2R / LOP3 / ISETP: ~250 extra instructions per product),
+// with or without the LEAD throttle below.  The carry-free 29-bit form (fr29.cuh)
+// is slower than fr.cuh for a lone warp too (mul 1054, sqr 880 cycles).
+// profiles/r02_lone_warp_latency.md has the numbers.
+//
 // Latency-oriented variants of the field primitives of fr.cuh, for code that runs
 // ONE warp per SM sub-partition (the warp-cooperative kernel of the tree levels
 // near the root, coop.cuh).

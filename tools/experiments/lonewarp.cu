@@ -1,7 +1,7 @@
 // Lone-warp issue rate of IMAD.WIDE.U32 as a function of the number of independent
 // dependency chains, and the latency of the field primitives when one warp has a
 // sub-partition to itself (the regime of the tree levels near the root).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I infimum_b200/csrc tools/experiments/lonewarp.cu -o tools/_bin/lonewarp
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I infimum_b200/csrc -I tools/experiments tools/experiments/lonewarp.cu -o tools/_bin/lonewarp
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "fr_lat.cuh"
