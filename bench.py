@@ -11,12 +11,19 @@ same line also carries, measured in the same process:
 
   e2e          the same metric through the public host-buffer API
                (infimum_b200.Poseidon.hash_batch -> inf_poseidon_hash_batch),
-               pinned host input -> device -> pinned host output every step
-  tree_merge   the 2^24-leaf binary poll-tree merge (16 777 215 hash2), device
-               timed, leaves sharded over the N GPUs as contiguous subtrees with
-               ONE all-gather (NCCL) of subtree roots and the top finished on
-               every rank (strong scaling; BASELINE.json's second metric)
-  roofline     integer-multiply roofline of the hash kernel (north star)
+               pinned host input -> device -> pinned host output every step;
+               beside it (same key, so the driver keeps them): pageable buffers,
+               the tree from host leaves, the replay raw messages -> root, and
+               the in-library multi-GPU merge (inf_multi_tree_merge) from host leaves
+  roofline     integer-multiply roofline of the hash kernel (north star), with
+               roofline.tree_merge = BASELINE.json's second metric: the 2^24-leaf
+               binary poll-tree merge (16 777 215 hash2), device timed, leaves
+               sharded over the N GPUs as contiguous subtrees with ONE all-gather
+               (NCCL) of subtree roots and the top finished on every rank (strong
+               scaling), and the 2^20-registration state tree sharded the same way
+               with its root checked against the oracle at every N
+               (roofline.tree_merge.bit_exact_tree); roofline.configs = the other
+               BASELINE configs
   cpu_baseline the C oracle ("port" of the Rust path) on the host cores, N=1
 
 --impl reference times the CPU restatement of the reference's own path
@@ -42,6 +49,7 @@ if ROOT not in sys.path:
 LOG_PAIRS = 24                      # 2^24 hash2 per GPU per step
 LOG_LEAVES = 24                     # 2^24-leaf poll tree
 W_HASH2 = 218592                    # IMAD-equivalents per hash2 of the reference algorithm
+W_HASH5, W_HASH4 = 731808, 528000
 IMAD_PER_CLK_PER_SM = 64            # CUDA programming guide, 32-bit integer multiply-add, cc 10.0
 METRIC = "Poseidon-BN254 hashes/s"
 
@@ -306,74 +314,60 @@ def run_ours(args, rank, world, local_rank):
     props = torch.cuda.get_device_properties(dev)
     sms_peak = props.multi_processor_count * IMAD_PER_CLK_PER_SM * 1965.0e6 / 1e12
 
-    # ---- tree merge of the 2^24-leaf poll tree, sharded over the ranks ----------------------
-    n_leaves = 1 << args.log_leaves
-    plan = sharded.make_plan(2, args.log_leaves, n_leaves, prepend_blank_leaf=False, to_depth=True, world=world)
-    lo, hi = plan.leaf_range(rank)
+    # ---- tree merges sharded over the ranks: the 2^24-leaf poll tree (headline) and the 2^20-registration
+    # ---- state tree, whose root is checked against the oracle at every N ------------------------------------
     del d_in
-    leaves = device_random_fr_range(lo, hi, dev, seed=77)
     backend = sharded.GpuBackend(ctx)
-    tree_ms, root = [], None
-    for it in range(2 + 3):
-        barrier()
-        with torch.cuda.stream(stream):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            root = sharded.sharded_tree_merge(leaves, plan, backend)
-            e1.record(stream)
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if it >= 2:
-            tree_ms.append(float(t.item()))
+
+    def sharded_ms(arity, full_depth, n_lv, blank, to_depth, seed, reps=3, warm=2):
+        pl = sharded.make_plan(arity, full_depth, n_lv, prepend_blank_leaf=blank, to_depth=to_depth, world=world)
+        a, b = pl.leaf_range(rank)
+        lv = device_random_fr_range(a, b, dev, seed=seed)
+        times, r = [], None
+        for it in range(warm + reps):
+            barrier()
+            with torch.cuda.stream(stream):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                r = sharded.sharded_tree_merge(lv, pl, backend)
+                e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it >= warm:
+                times.append(float(t.item()))
+        del lv
+        return times, r.cpu().numpy().tobytes().hex(), pl
+
+    n_leaves = 1 << args.log_leaves
+    tree_ms, root_hex, plan = sharded_ms(2, args.log_leaves, n_leaves, False, True, 77)
     tree_best = min(tree_ms)
     n_tree_hashes = n_leaves - 1
-    root_hex = bytes(root.cpu().numpy().tobytes()).hex()
+    st_ms, st_root, st_plan = sharded_ms(2, 32, 1 << 20, True, False, 20, reps=5)
+    bit_exact_tree = None
+    if rank == 0:
+        # every rank generated its slice of the same seeded leaf array; rank 0 rebuilds all of it and asks the
+        # oracle (dense tree over blank leaf + 2^20 leaves, all host threads: about a second)
+        from oracle import c_oracle
+        allv = device_random_fr(1 << 20, dev, seed=20).cpu().numpy()
+        blank = np.frombuffer(ib.get_merkle_zeroes(2, ctx)[0], dtype=np.uint8).reshape(1, 32)
+        bit_exact_tree = c_oracle.dense_tree_root(2, 21, np.concatenate([blank, allv])).hex() == st_root
+        del allv
 
-    # ---- BASELINE configs[3] / [2] sharded the same way when there is more than one rank ---------
     sharded_extras = {}
     if world > 1 and not args.no_extras:
-        del leaves
         torch.cuda.empty_cache()
-
-        def sharded_ms(arity, full_depth, n_lv, blank, to_depth, seed):
-            pl = sharded.make_plan(arity, full_depth, n_lv, prepend_blank_leaf=blank, to_depth=to_depth, world=world)
-            a, b = pl.leaf_range(rank)
-            lv = device_random_fr_range(a, b, dev, seed=seed)
-            best, r = None, None
-            for it in range(3):
-                barrier()
-                with torch.cuda.stream(stream):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(stream)
-                    r = sharded.sharded_tree_merge(lv, pl, backend)
-                    e1.record(stream)
-                barrier()
-                t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                if it >= 1:
-                    best = float(t.item()) if best is None else min(best, float(t.item()))
-            return best, r.cpu().numpy().tobytes().hex(), pl
-
-        ms, rh, pl = sharded_ms(5, 12, 1 << 26, False, True, 26)
+        ms, rh, pl = sharded_ms(5, 12, 1 << 26, False, True, 26, reps=2, warm=1)
         sharded_extras["message_tree_2^26_sharded"] = {
-            "ms": ms, "n_gpus": world, "hashes": 16777220, "hashes_per_s": 16777220 / (ms * 1e-3), "root": rh,
-            "shard_level": pl.level, "subtrees": pl.n_subtrees,
-            "subtrees_per_rank": [e - b for b, e in pl.subtree_ranges]}
-        ms, rh, pl = sharded_ms(2, 32, 1 << 20, True, False, 20)
-        sharded_extras["state_tree_2^20_sharded"] = {
-            "ms": ms, "n_gpus": world, "hashes": (1 << 20) + 20, "root": rh, "shard_level": pl.level,
-            "subtrees_per_rank": [e - b for b, e in pl.subtree_ranges], "depth_field": pl.insert_depth,
-            "root_depth": pl.root_depth}
-        leaves = torch.empty((0, 32), dtype=torch.uint8, device=dev)
+            "ms": min(ms), "n_gpus": world, "hashes": 16777220, "hashes_per_s": 16777220 / (min(ms) * 1e-3), "root": rh,
+            "shard_level": pl.level, "subtrees": pl.n_subtrees}
 
     # ---- the other BASELINE configs and the "next" rows, rank 0 only, short ---------------------
-    extras = {}
-    if rank == 0 and not args.no_extras:
-        del leaves
+    extras, e2e_more = {}, {}
+    props = torch.cuda.get_device_properties(dev)
+    if rank == 0 and not args.no_extras and world == 1:
         torch.cuda.empty_cache()
-        W_HASH5, W_HASH4 = 731808, 528000
 
         def timed(fn, reps=3):
             fn()
@@ -390,6 +384,16 @@ def run_ours(args, rank, world, local_rank):
                 best = ms if best is None else min(best, ms)
             return best
 
+        def wall(fn, reps=3):
+            best = None
+            for _ in range(reps):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                fn()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            return best * 1e3
+
         def merge_dev_ms(arity, full_depth, lv, blank, to_depth):
             root = C.create_string_buffer(32)
             idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
@@ -401,13 +405,10 @@ def run_ours(args, rank, world, local_rank):
                 assert rc in (0, 2), rc
             return timed(run), root.raw.hex(), idp.value, rdp.value
 
-        # configs[2]: state-tree merge of 2^20 registrations (+ blank leaf): depth field 20, root depth 21
-        lv = device_random_fr(1 << 20, dev, seed=20)
-        ms, root_hex2, idp, rdp = merge_dev_ms(2, 32, lv, True, False)
-        nh = (1 << 20) + 20            # 2^20 + 20 parents for 2^20 + 1 logical leaves
-        extras["state_tree_2^20"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
-                                     "root_depth": rdp, "roofline_frac": nh * W_HASH2 / (ms * 1e-3) / 1e12 / (sms_peak),
-                                     "root": root_hex2}
+        # small trees: the regime the reference's dev runtime lives in (65 536 participants)
+        lv = device_random_fr(1 << 16, dev, seed=16)
+        ms, _, _, _ = merge_dev_ms(2, 32, lv, True, False)
+        extras["state_tree_2^16"] = {"ms": ms, "hashes": (1 << 16) + 16}
         # configs[3] on one GPU: message-tree merge of 2^26 interaction leaves, arity 5, depth 12
         lv = device_random_fr(1 << 26, dev, seed=26)
         ms, root_hex5, idp, rdp = merge_dev_ms(5, 12, lv, False, True)
@@ -416,42 +417,37 @@ def run_ours(args, rank, world, local_rank):
             c = -(-c // 5)
             nh += c
         extras["message_tree_2^26"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
-                                       "root_depth": rdp, "roofline_frac": nh * W_HASH5 / (ms * 1e-3) / 1e12 / (sms_peak),
-                                       "root": root_hex5}
-        # end to end for the tree: 2^24 leaves in pinned host memory -> root (inf_tree_merge uploads in
-        # chunks that overlap with level-0 hashing)
+                                       "root_depth": rdp, "root": root_hex5}
+        # end to end for the tree: 2^24 leaves in host memory -> root (inf_tree_merge uploads in chunks that
+        # overlap with level-0 hashing), pinned and pageable
         h_leaves = torch.empty((1 << 24, 32), dtype=torch.uint8).pin_memory()
         h_leaves.copy_(lv[: 1 << 24])
-        hl = h_leaves.numpy()
         root = C.create_string_buffer(32)
         idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
-        best = None
-        for _ in range(3):
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            rc = ctx.lib.inf_tree_merge(ctx.handle, 2, 24, 0, 1, hl.ctypes.data, 1 << 24, root, C.byref(idp),
-                                        C.byref(rdp), C.byref(has))
-            dt = time.perf_counter() - t0
-            assert rc in (0, 2), rc
-            best = dt if best is None else min(best, dt)
-        extras["tree_merge_2^24_e2e"] = {"ms": best * 1e3, "h2d_bytes": (1 << 24) * 32, "d2h_bytes": 32,
-                                         "api": "inf_tree_merge (pinned host leaves -> root)", "root": root.raw.hex()}
-        del h_leaves, hl
+
+        def tree_from(arr):
+            def run():
+                rc = ctx.lib.inf_tree_merge(ctx.handle, 2, 24, 0, 1, arr.ctypes.data, 1 << 24, root, C.byref(idp),
+                                            C.byref(rdp), C.byref(has))
+                assert rc in (0, 2), rc
+            return run
+        hl = h_leaves.numpy()
+        pinned_ms = wall(tree_from(hl))
+        pg = np.empty((1 << 24, 32), dtype=np.uint8)
+        pg[:] = hl
+        pageable_ms = wall(tree_from(pg))
+        e2e_more["tree_merge_2^24"] = {"ms_pinned": pinned_ms, "ms_pageable": pageable_ms, "h2d_bytes": (1 << 24) * 32,
+                                       "d2h_bytes": 32, "api": "inf_tree_merge (host leaves -> root)", "root": root.raw.hex()}
+        del h_leaves, hl, pg
         # what a caller with ordinary (pageable) buffers sees: hash2 over 2^22 pairs, numpy arrays in and out
-        import numpy as np
         npg = 1 << 22
         pg_in = np.empty((2 * npg, 32), dtype=np.uint8)
         pg_in[:] = lv[: 2 * npg].cpu().numpy()
         pg_out = np.empty((npg, 32), dtype=np.uint8)
         h2.hash_batch(pg_in, npg, out=pg_out)
-        best = None
-        for _ in range(3):
-            t0 = time.perf_counter()
-            h2.hash_batch(pg_in, npg, out=pg_out)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        extras["hash2_2^22_e2e_pageable"] = {"ms": best * 1e3, "hashes_per_s": npg / best,
-                                             "api": "inf_poseidon_hash_batch (pageable host buffers)"}
+        ms = wall(lambda: h2.hash_batch(pg_in, npg, out=pg_out))
+        e2e_more["hash2_2^22_pageable"] = {"ms": ms, "hashes_per_s": npg / (ms * 1e-3),
+                                           "api": "inf_poseidon_hash_batch (pageable host buffers)"}
         del pg_in, pg_out
         # hash5 batch (t = 6), 2^22 tuples
         n5 = 1 << 22
@@ -459,8 +455,7 @@ def run_ours(args, rank, world, local_rank):
         o5 = torch.empty((n5, 32), dtype=torch.uint8, device=dev)
         h5 = ib.Poseidon.new_circom(5, ctx)
         ms = timed(lambda: h5.hash_batch_device(d5.data_ptr(), n5, o5.data_ptr(), stream.cuda_stream))
-        extras["hash5_2^22"] = {"ms": ms, "hashes_per_s": n5 / (ms * 1e-3),
-                                "roofline_frac": n5 * W_HASH5 / (ms * 1e-3) / 1e12 / sms_peak}
+        extras["hash5_2^22"] = {"ms": ms, "hashes_per_s": n5 / (ms * 1e-3)}
         # next row: fused interaction-leaf hashing, 2^20 messages (2 x hash5 + hash4 each)
         nm = 1 << 20
         pk, dat = lv[: 2 * nm], lv[2 * nm: 12 * nm]
@@ -470,16 +465,65 @@ def run_ours(args, rank, world, local_rank):
             rc = ctx.lib.inf_interaction_leaves_dev(ctx.handle, pk.data_ptr(), dat.data_ptr(), nm, ol.data_ptr(),
                                                     stream.cuda_stream)
             assert rc == 0
-        ms = timed(leaf_run)
-        extras["interaction_leaves_2^20"] = {"ms": ms, "messages_per_s": nm / (ms * 1e-3),
-                                             "roofline_frac": nm * (2 * W_HASH5 + W_HASH4) / (ms * 1e-3) / 1e12 / sms_peak}
-        del lv, d5, o5, pk, dat, ol
+        leaf_ms = timed(leaf_run)
+        extras["interaction_leaves_2^20"] = {"ms": leaf_ms, "messages_per_s": nm / (leaf_ms * 1e-3)}
+        ms5, _, _, _ = merge_dev_ms(5, 9, ol, False, True)
+        # replay: raw messages in host memory -> leaves -> merged tree, nothing but the root coming back
+        # (inf_replay_interactions); compared with leaf time + tree time on device-resident data
+        for log_m, kinds in ((20, ("pinned", "pageable")), (24, ("pinned",))):
+            m = 1 << log_m
+            h_pk = torch.empty((m, 64), dtype=torch.uint8).pin_memory()
+            h_dat = torch.empty((m, 320), dtype=torch.uint8).pin_memory()
+            for b0 in range(0, m, 1 << 22):          # the 12 elements of a message come from one seeded block
+                blk = device_random_fr(12 * min(1 << 22, m - b0), dev, seed=900 + b0 // (1 << 22))
+                k = blk.shape[0] // 12
+                h_pk[b0:b0 + k].copy_(blk[: 2 * k].view(k, 64))
+                h_dat[b0:b0 + k].copy_(blk[2 * k:].view(k, 320))
+                del blk
+            row = {"messages": m, "h2d_bytes": m * 384, "d2h_bytes": 32}
+            depth_m = next(d for d in range(40) if 5 ** d >= m)
+            for kind in kinds:
+                a_pk, a_dat = h_pk.numpy(), h_dat.numpy()
+                if kind == "pageable":
+                    a_pk, a_dat = a_pk.copy(), a_dat.copy()
+                res = {}
 
+                def run():
+                    t, ep, et, _, _ = ib.replay_interactions(depth_m, a_pk, a_dat, 0, 2, 1, ctx)
+                    res["root"] = t.root.hex()
+                run()
+                row["ms_" + kind] = wall(run, reps=2)
+                row["root"] = res["root"]
+            row["messages_per_s"] = m / (row["ms_pinned"] * 1e-3)
+            if log_m == 20:
+                row["leaf_ms_plus_tree_ms_device"] = leaf_ms + ms5
+            e2e_more["replay_interactions_2^%d" % log_m] = row
+            del h_pk, h_dat
+        del lv, d5, o5, pk, dat, ol
+        torch.cuda.empty_cache()
+
+    # ---- the in-library multi-GPU path (inf_multi_*: ONE process drives all N GPUs; what a Rust host calls),
+    # ---- from host leaves, in a child process of rank 0 once the ranks are through --------------------------
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
+    torch.cuda.empty_cache()
+    multi = None
+    if not args.no_extras:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--multi-leg", "--gpus", str(world),
+                                  "--log-leaves", str(args.log_leaves)], capture_output=True, text=True, timeout=600)
+            multi = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else \
+                {"error": (out.stderr or out.stdout)[-300:]}
+        except Exception as e:                                   # noqa: BLE001
+            multi = {"error": repr(e)[:300]}
+        if multi is not None and "ms_pinned" in multi:
+            multi["over_device_timed_sharded"] = multi["ms_pinned"] / tree_best
+        e2e_more["tree_merge_multi"] = multi
 
     # ---- roofline of the dominant kernel (hash_batch_kernel<t=3>) ------------------------------
-    props = torch.cuda.get_device_properties(dev)
     sms = props.multi_processor_count
     sm_max_mhz = clocks.get("sm_max_mhz") or 1965.0
     peak = sms * IMAD_PER_CLK_PER_SM * sm_max_mhz * 1e6 / 1e12          # T IMAD/s at the max SM clock
@@ -500,47 +544,79 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
     traffic = None
-    tf = os.path.join(ROOT, "profiles", "r01_hash2_traffic.json")
-    if os.path.exists(tf):
+    for tf in ("r02_hash2_traffic.json", "r01_hash2_traffic.json"):
+        tf = os.path.join(ROOT, "profiles", tf)
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                break
+            except Exception:
+                pass
+    gbs = n * 96 / (avg_launch_ms * 1e-3) / 1e9
+
+    # executed work: multiply-pipe instructions of ONE hash counted in the SASS of the shipped kernels
+    # (tools/sass_count.py: IMAD.WIDE(.X) and IMAD.HI occupy the pipe 4 cycles per warp, IMAD 2), against the
+    # pipe's capacity of one warp-cycle per sub-partition per clock
+    def executed_of(obj, fn, trips, fallback):
+        ex = dict(fallback, source="static (tools/sass_count.py)")
         try:
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import sass_count
+            live = sass_count.count(os.path.join(ROOT, "infimum_b200", "_build", obj), fn, trips)
+            ex = {"imad_wide": live["wide"], "imad_hi": live["hi"], "imad": live["imad"],
+                  "all_instructions": sum(live.values()), "source": "cuobjdump -sass of the shipped " + obj}
         except Exception:
             pass
-    gbs = n * 96 / (avg_launch_ms * 1e-3) / 1e9
+        cyc = 4 * (ex["imad_wide"] + ex["imad_hi"]) + 2 * ex["imad"]
+        ex["pipe_cycles_per_hash_per_warp"] = cyc
+        ex["pipe_bound_hashes_per_s"] = sms * 4 * sm_max_mhz * 1e6 / cyc * 32   # the multiply pipe never idle
+        return ex
+
+    ex3 = executed_of("poseidon_t3.o", "hash_batch_kernelILb0", [4, 28, 3], {"imad_wide": 53145, "imad_hi": 3056, "imad": 3056})
+    ex3t = executed_of("poseidon_t3.o", "tree_level_kernel", [4, 28, 3], {"imad_wide": 53145, "imad_hi": 3056, "imad": 3056})
+    ex6 = executed_of("poseidon_t6.o", "hash_batch_kernelILb0", [4, 30, 3], {"imad_wide": 104434, "imad_hi": 4656, "imad": 4657})
+    ex6t = executed_of("poseidon_t6.o", "tree_level_kernel", [4, 30, 3], {"imad_wide": 104434, "imad_hi": 4656, "imad": 4657})
+    rate = n / (avg_launch_ms * 1e-3)
+    ex3.update({"frac_of_pipe_bound": rate / ex3["pipe_bound_hashes_per_s"],
+                "wide_per_s": ex3["imad_wide"] * rate / 1e12,
+                "wide_per_s_measured_peak": (meas.get("imad_wide_carry_chain_x2") or 0) / 2 or None})
+    for k, ex in (("hash5_2^22", ex6), ("message_tree_2^26", ex6t)):
+        if k in extras:
+            extras[k]["frac_of_pipe_bound"] = extras[k]["hashes_per_s"] / ex["pipe_bound_hashes_per_s"]
+            extras[k]["roofline_frac"] = extras[k]["hashes_per_s"] * W_HASH5 / 1e12 / peak
+    if "interaction_leaves_2^20" in extras:
+        extras["interaction_leaves_2^20"]["roofline_frac"] = \
+            extras["interaction_leaves_2^20"]["messages_per_s"] * (2 * W_HASH5 + W_HASH4) / 1e12 / peak
+    for k, v in sharded_extras.items():
+        v["frac_of_pipe_bound"] = v["hashes_per_s"] / (world * ex6t["pipe_bound_hashes_per_s"])
+    tree = {"leaves": n_leaves, "hashes": n_tree_hashes, "ms": tree_best, "ms_all": tree_ms, "n_gpus": world,
+            "scaling": "strong", "hashes_per_s": n_tree_hashes / (tree_best * 1e-3),
+            "frac_of_pipe_bound": n_tree_hashes / (tree_best * 1e-3) / (world * ex3t["pipe_bound_hashes_per_s"]),
+            "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / (peak * world),
+            "shard_level": plan.level, "subtrees": plan.n_subtrees,
+            "collective": "one all_gather of <=%d x 32 B subtree roots per rank (NCCL)" %
+                          max(e - b for b, e in plan.subtree_ranges) if world > 1 else "none (1 GPU)",
+            "root": root_hex,
+            "state_tree_2^20": {"ms": min(st_ms), "hashes": (1 << 20) + 20, "depth_field": st_plan.insert_depth,
+                                "root_depth": st_plan.root_depth, "shard_level": st_plan.level, "root": st_root,
+                                "frac_of_pipe_bound": ((1 << 20) + 20) / (min(st_ms) * 1e-3) /
+                                                      (world * ex3t["pipe_bound_hashes_per_s"])},
+            "bit_exact_tree": bit_exact_tree,
+            "bit_exact_tree_what": "root of the 2^20-registration state tree merged over %d GPU(s) == oracle" % world}
     roofline = {
         "bound": "imad", "achieved": achieved, "peak": peak, "unit": "TIMAD/s", "frac": achieved / peak,
-        "traffic": traffic,
+        "frac_executed": ex3["frac_of_pipe_bound"], "traffic": traffic,
         "kernel": "hash_batch_kernel<t=3> (one launch per step)",
         "work_per_launch": "2^%d hash2 x W=%d IMAD-eq (reference algorithm: 828 field mults x 264)" % (args.log_pairs, W_HASH2),
         "peak_source": "theoretical: %d SMs x 64 IMAD/clk x %.0f MHz (BASELINE.md 2)" % (sms, sm_max_mhz),
         "peak_measured": meas, "frac_of_measured_imad": achieved / meas["imad"] if meas.get("imad") else None,
         "avg_launch_ms": avg_launch_ms,
-        "note": "frac is reference-equivalent work: the kernel runs the sparse/lazy/paired schedule (594 field "
-                "mults, 162 of them squarings, ~62.5k IMAD-pipe instructions per hash2), so frac may exceed 1; "
-                "executed multiply-pipe utilisation (96 % busy) is in profiles/r01_hash2_ncu_summary.md",
+        "note": "frac = reference-algorithm work (SURVEY 8d; the kernel runs a sparse/lazy schedule, so it can exceed 1); "
+                "frac_executed = measured rate / multiply-pipe bound of the executed SASS",
+        "executed": ex3, "executed_t6": ex6, "tree_merge": tree, "configs": dict(extras, **sharded_extras),
         "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "bytes_per_hash": 96},
     }
-    # executed work: multiply-pipe instructions of ONE hash2 counted in the SASS of the shipped kernel
-    # (tools/sass_count.py: IMAD.WIDE(.X) and IMAD.HI occupy the pipe 4 cycles per warp, IMAD 2), against the
-    # pipe's capacity of one warp-cycle per sub-partition per clock
-    executed = {"imad_wide": 56793, "imad_hi": 3056, "imad": 3056, "source": "static (tools/sass_count.py, round 1)"}
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import sass_count
-        live = sass_count.count(os.path.join(ROOT, "infimum_b200", "_build", "poseidon_t3.o"), "hash_batch_kernelILb0",
-                                [4, 28, 3])
-        executed = {"imad_wide": live["wide"], "imad_hi": live["hi"], "imad": live["imad"],
-                    "all_instructions": sum(live.values()), "source": "cuobjdump -sass of the shipped poseidon_t3.o"}
-    except Exception:
-        pass
-    pipe_cycles = 4 * (executed["imad_wide"] + executed["imad_hi"]) + 2 * executed["imad"]
-    pipe_bound = sms * 4 * sm_max_mhz * 1e6 / pipe_cycles * 32          # hashes/s with the multiply pipe never idle
-    executed.update({"pipe_cycles_per_hash_per_warp": pipe_cycles, "pipe_bound_hashes_per_s": pipe_bound,
-                     "frac_of_pipe_bound": (n / (avg_launch_ms * 1e-3)) / pipe_bound,
-                     "wide_per_s": executed["imad_wide"] * n / (avg_launch_ms * 1e-3) / 1e12,
-                     "wide_per_s_measured_peak": (meas.get("imad_wide_carry_chain_x2") or 0) / 2 or None})
-    roofline["executed"] = executed
     base, _, _ = cpu_baseline_hash2(12.0) if world == 1 and not args.no_cpu_baseline else (None, 0, 0)
 
     line = {
@@ -553,23 +629,58 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (1 GiB) larger than L2 (126 MB); no flush needed",
                    "parallelism": "replicas x%d, no collective" % world},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "hashes/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 32,
-                "steps": e2e_steps, "api": "infimum_b200.Poseidon.hash_batch -> inf_poseidon_hash_batch (pinned host buffers)",
-                "matches_device_run": e2e_ok},
+        "e2e": dict({"value": e2e_value, "unit": "hashes/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 32,
+                     "steps": e2e_steps,
+                     "api": "infimum_b200.Poseidon.hash_batch -> inf_poseidon_hash_batch (pinned host buffers)",
+                     "matches_device_run": e2e_ok}, **e2e_more),
         "roofline": roofline,
-        "tree_merge": {"leaves": n_leaves, "hashes": n_tree_hashes, "ms": tree_best, "ms_all": tree_ms,
-                       "hashes_per_s": n_tree_hashes / (tree_best * 1e-3), "n_gpus": world, "scaling": "strong",
-                       "shard_level": plan.level, "subtrees": plan.n_subtrees,
-                       "collective": "one all_gather of <=%d x 32 B subtree roots per rank (NCCL)" %
-                                     max(e - b for b, e in plan.subtree_ranges) if world > 1 else "none (1 GPU)",
-                       "roofline_frac": n_tree_hashes * W_HASH2 / (tree_best * 1e-3) / 1e12 / (peak * world),
-                       "root": root_hex},
-        "bit_exact_sample": ok,
-        "other_configs": dict(extras, **sharded_extras),
+        "tree_merge_ms": tree_best, "bit_exact_sample": ok, "bit_exact_tree": bit_exact_tree,
     }
     if base:
         line["cpu_baseline"] = base
     _emit(json.dumps(line))
+    return 0
+
+
+def run_multi_leg(args):
+    """Child of rank 0: ONE process drives all N GPUs through inf_multi_* (the form the Rust shim
+    calls): 2^24-leaf binary tree from host leaves, pinned and pageable, and the 2^20-registration
+    state tree with its root checked against the oracle.  Prints one JSON object."""
+    import numpy as np
+    import torch
+    from infimum_b200.multi import MultiGpu
+    from oracle import c_oracle
+    import infimum_b200 as ib
+    G = args.gpus
+    dev = torch.device("cuda", 0)
+    n = 1 << args.log_leaves
+    out = {"n_gpus": G, "leaves": n, "api": "inf_multi_tree_merge (host leaves -> root, %d device(s), one process)" % G}
+    h = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    h.copy_(device_random_fr(n, dev, seed=77))
+    hl = h.numpy()
+    mg = MultiGpu(list(range(G)))
+
+    def best_of(arr, reps=3):
+        best, root = None, None
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            root, _, _, rc = mg.tree_merge(2, args.log_leaves, arr, False, True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best * 1e3, root.hex()
+    out["ms_pinned"], out["root"] = best_of(hl)
+    pg = hl.copy()
+    out["ms_pageable"], _ = best_of(pg, reps=2)
+    del pg
+    st = device_random_fr(1 << 20, dev, seed=20).cpu().numpy()
+    root, idp, rdp, rc = mg.tree_merge(2, 32, st, True, False)
+    blank = np.frombuffer(ib.get_merkle_zeroes(2)[0], dtype=np.uint8).reshape(1, 32)
+    out["bit_exact_tree"] = bool(c_oracle.dense_tree_root(2, 21, np.concatenate([blank, st])) == root)
+    t0 = time.perf_counter()
+    mg.tree_merge(2, 32, st, True, False)
+    out["state_tree_2^20_ms_pageable"] = (time.perf_counter() - t0) * 1e3
+    mg.close()
+    print(json.dumps(out))
     return 0
 
 
@@ -583,7 +694,10 @@ def main():
     ap.add_argument("--log-leaves", type=int, default=LOG_LEAVES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs / next-row timings")
+    ap.add_argument("--multi-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.multi_leg:
+        return run_multi_leg(args)
 
     world = _env_int("WORLD_SIZE", 1)
     rank = _env_int("RANK", 0)

@@ -85,6 +85,20 @@ const char* inf_last_cuda_error(const inf_ctx* ctx);
 /* Library version / build info. */
 const char* inf_version(void);
 
+/* ---- host buffers ---------------------------------------------------------------
+ * Host-buffer calls accept any host memory.  Page-locked buffers are copied by
+ * DMA straight from / into the caller's memory; pageable buffers (a Vec<u8>, a
+ * numpy array) are staged through pinned memory inside the library by helper
+ * threads, which costs host memory bandwidth but keeps the pipeline full
+ * (bench.py: e2e.hash2_2^22_pageable next to e2e.value).  A caller that keeps its
+ * buffers for many calls can take them from inf_host_alloc (cudaHostAlloc,
+ * portable) or pin its own with inf_host_register (cudaHostRegister; pinning
+ * costs about as much as one copy, so it pays only for buffers that are reused). */
+int inf_host_alloc(inf_ctx* ctx, size_t bytes, void** out);
+int inf_host_free(inf_ctx* ctx, void* p);
+int inf_host_register(inf_ctx* ctx, void* p, size_t bytes);
+int inf_host_unregister(inf_ctx* ctx, void* p);
+
 /* ---- Poseidon hasher --------------------------------------------------------
  * Replaces Poseidon::<Fr>::new_circom(n_inputs) / with_domain_tag_circom
  * (poseidon.rs:302-327) followed by PoseidonHasher::hash (poseidon.rs:162-208)

@@ -49,6 +49,7 @@ EXPORTS = [
     "inf_measure_imad_peak", "inf_poseidon_hash_batch_params",
     "inf_tree_append", "inf_tree_append_dev", "inf_tree_merge_frontier",
     "inf_tree_node_paths", "inf_tree_level_nodes", "inf_replay_registrations", "inf_replay_interactions",
+    "inf_host_alloc", "inf_host_free", "inf_host_register", "inf_host_unregister",
 ]
 
 _lib = None
@@ -138,6 +139,14 @@ def load() -> C.CDLL:
     lib.inf_replay_interactions.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, ip,
                                             u32p, u32p, u32p, vp, C.POINTER(vp)]
     lib.inf_replay_interactions.restype = C.c_int
+    lib.inf_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.inf_host_alloc.restype = C.c_int
+    lib.inf_host_free.argtypes = [vp, vp]
+    lib.inf_host_free.restype = C.c_int
+    lib.inf_host_register.argtypes = [vp, vp, C.c_size_t]
+    lib.inf_host_register.restype = C.c_int
+    lib.inf_host_unregister.argtypes = [vp, vp]
+    lib.inf_host_unregister.restype = C.c_int
     lib.inf_tree_destroy.argtypes = [vp]
     lib.inf_tree_destroy.restype = None
     lib.inf_merkle_roots_from_paths.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]

@@ -12,6 +12,7 @@
 #include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_params.h"
@@ -47,6 +48,9 @@ struct inf_ctx {
     void* io[2] = {nullptr, nullptr};          // staging for host-buffer calls
     size_t io_bytes[2] = {0, 0};
     void* d_front = nullptr;                   // frontier entries on the device: 33 levels x 4 nodes (+ 1 scratch node)
+    void* bounce = nullptr;                    // pinned staging for callers with pageable buffers
+    size_t bounce_bytes = 0;
+    cudaEvent_t bounce_done[3][2] = {};        // per pipeline stream, per half of its staging
     uint32_t* d_dense[14] = {};
     uint8_t zeroes[2][33][32];                 // [0] binary, [1] quinary (zeroes.rs)
     std::string last_cuda_error;
@@ -677,6 +681,10 @@ void inf_destroy(inf_ctx* ctx) {
             if (ctx->io[i]) cudaFree(ctx->io[i]);
         }
         if (ctx->d_front) cudaFree(ctx->d_front);
+        if (ctx->bounce) cudaFreeHost(ctx->bounce);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 2; j++)
+                if (ctx->bounce_done[i][j]) cudaEventDestroy(ctx->bounce_done[i][j]);
         for (int t = 0; t < 14; t++)
             if (ctx->d_dense[t]) cudaFree(ctx->d_dense[t]);
         for (int i = 0; i < 3; i++) {
@@ -700,6 +708,97 @@ int inf_poseidon_hash_batch_dev(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags,
                           stream ? (cudaStream_t)stream : ctx->stream, false);
 }
 
+// Is this host pointer ordinary pageable memory (neither cudaHostAlloc'ed nor cudaHostRegister'ed)?
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// The same batch for callers whose buffers are pageable (a Rust Vec<u8>, a numpy array).  A copy
+// from or to pageable memory is staged by the calling thread and blocks it, which serialises
+// upload, hashing and read-back (measured -12 %: 124.6 vs 139.9 M hash2/s in round 1).  Here each
+// of the three pipeline streams gets a host thread of its own and two halves of pinned staging:
+// the thread copies chunk j into pinned memory while chunk j-1 of its stream is being hashed and
+// copies results out of pinned memory one chunk late, so the three threads together move the
+// ~14 GB/s the GPU consumes and nothing in the loop waits for the device except on a chunk that
+// is already one behind.
+static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
+                               const uint8_t* in, uint64_t n, uint8_t* out, bool dense, const CustomParams* custom) {
+    const uint64_t chunk = 1ull << 18;
+    const size_t in_row = (size_t)n_inputs * 32, slot = chunk * (in_row + 32);
+    int rc;
+    if (ctx->bounce_bytes < 6 * slot) {
+        if (ctx->bounce) CU(cudaFreeHost(ctx->bounce));
+        ctx->bounce = nullptr;
+        ctx->bounce_bytes = 0;
+        CU(cudaHostAlloc(&ctx->bounce, 6 * slot, cudaHostAllocDefault));
+        ctx->bounce_bytes = 6 * slot;
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 2; j++)
+            if (!ctx->bounce_done[i][j]) CU(cudaEventCreateWithFlags(&ctx->bounce_done[i][j], cudaEventDisableTiming));
+    // device staging: every chunk in flight has its own region (3 streams x 2 halves)
+    if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 6 * chunk * in_row))) return rc;
+    if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], 6 * chunk * 32))) return rc;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    int rcs[3] = {INF_OK, INF_OK, INF_OK};
+    cudaError_t errs[3] = {cudaSuccess, cudaSuccess, cudaSuccess};
+    auto worker = [&](int i) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) {
+            rcs[i] = INF_ERR_NO_DEVICE;
+            return;
+        }
+        cudaStream_t st = ctx->pipe[i];
+        cudaError_t e = cudaSuccess;
+        auto region = [&](int half, char** h_in, char** h_out, char** d_in, char** d_out) {
+            const int r = 2 * i + half;
+            *h_in = (char*)ctx->bounce + (size_t)r * slot;
+            *h_out = *h_in + chunk * in_row;
+            *d_in = (char*)ctx->io[0] + (size_t)r * chunk * in_row;
+            *d_out = (char*)ctx->io[1] + (size_t)r * chunk * 32;
+        };
+        uint64_t prev = UINT64_MAX;                             // this thread's previous chunk, results not yet copied out
+        int j = 0;
+        for (uint64_t k = i; k < n_chunks + 3 && e == cudaSuccess && !rcs[i]; k += 3, j++) {
+            char *h_in, *h_out, *d_in, *d_out;
+            if (k < n_chunks) {
+                const uint64_t off = k * chunk, c = std::min<uint64_t>(chunk, n - off);
+                region(j & 1, &h_in, &h_out, &d_in, &d_out);
+                // this half was last used by chunk j-2, whose results were copied out in iteration j-1
+                memcpy(h_in, in + off * in_row, c * in_row);
+                if ((e = cudaMemcpyAsync(d_in, h_in, c * in_row, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+                if ((rcs[i] = hash_batch_dev(ctx, n_inputs, flags, tag, d_in, c, d_out, st, dense, custom))) break;
+                if ((e = cudaMemcpyAsync(h_out, d_out, c * 32, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+                if ((e = cudaEventRecord(ctx->bounce_done[i][j & 1], st)) != cudaSuccess) break;
+            }
+            if (prev != UINT64_MAX) {
+                const uint64_t off = prev * chunk, c = std::min<uint64_t>(chunk, n - off);
+                region((j - 1) & 1, &h_in, &h_out, &d_in, &d_out);
+                if ((e = cudaEventSynchronize(ctx->bounce_done[i][(j - 1) & 1])) != cudaSuccess) break;
+                memcpy(out + off * 32, h_out, c * 32);
+            }
+            prev = k < n_chunks ? k : UINT64_MAX;
+        }
+        errs[i] = e;
+        cudaStreamSynchronize(st);                               // nothing of this call left in flight on return
+    };
+    {
+        std::thread t1(worker, 1), t2(worker, 2);
+        worker(0);
+        t1.join();
+        t2.join();
+    }
+    for (int i = 0; i < 3; i++) {
+        if (rcs[i]) return rcs[i];
+        if (errs[i] != cudaSuccess) return cuda_fail(ctx, errs[i], "pageable batch pipeline");
+    }
+    return INF_OK;
+}
+
 // Host-buffer batch: the batch is cut into chunks that rotate over three
 // streams, each doing H2D -> kernel -> D2H for its chunk, so that with pinned
 // host buffers the copies of one chunk hide behind the hashing of another (the
@@ -712,6 +811,8 @@ static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, cons
     if (n == 0) return INF_OK;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
+    if (n >= (1ull << 20) && (is_pageable(in) || is_pageable(out)))
+        return hash_batch_pageable(ctx, n_inputs, flags, tag, in, n, out, dense, custom);
     const uint64_t super = 1ull << 24;                 // device staging is sized for at most 2^24 hashes
     const uint64_t chunk = 1ull << 19;
     const size_t in_row = (size_t)n_inputs * 32;
@@ -858,6 +959,40 @@ int inf_interaction_leaves_dev(inf_ctx* ctx, const void* d_public_keys, const vo
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
     CU(launch_interaction_leaves(d_public_keys, d_data, d_leaves, n, stream ? (cudaStream_t)stream : ctx->stream));
+    return INF_OK;
+}
+
+int inf_host_alloc(inf_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return INF_ERR_NULL_POINTER;
+    *out = nullptr;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return INF_OK;
+}
+
+int inf_host_free(inf_ctx* ctx, void* p) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (!p) return INF_OK;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    CU(cudaFreeHost(p));
+    return INF_OK;
+}
+
+int inf_host_register(inf_ctx* ctx, void* p, size_t bytes) {
+    if (!ctx || !p) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return INF_OK;
+}
+
+int inf_host_unregister(inf_ctx* ctx, void* p) {
+    if (!ctx || !p) return INF_ERR_NULL_POINTER;
+    Bind bind(ctx);
+    if (!bind.ok) return INF_ERR_NO_DEVICE;
+    CU(cudaHostUnregister(p));
     return INF_OK;
 }
 

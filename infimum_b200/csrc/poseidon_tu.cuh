@@ -285,15 +285,16 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
     return cudaGetLastError();
 }
 
-// Levels with at most this many parents go to the warp-cooperative kernel (they
-// are latency-bound either way; measured best 16 384..32 768 on B200, tools/tree_probe.py;
-// INF_COOP_MAX overrides, 0 disables).
+// Levels with at most this many parents go to the warp-cooperative kernel: the measured
+// crossover with the per-thread kernel is 16 384 parents for hash2 (203 vs 196 us) and
+// between 8 192 and 16 384 for hash5 (profiles/r02_tree_levels.md, tools/level_probe.py).
+// INF_COOP_MAX overrides, 0 disables.
 static uint64_t coop_max() {
     static long long v = -1;
     static bool set_on[64] = {};
     if (v < 0) {
         const char* e = getenv("INF_COOP_MAX");
-        v = e ? atoll(e) : 16384;
+        v = e ? atoll(e) : (T >= 5 ? 8192 : 16384);
     }
     int dev = 0;
     cudaGetDevice(&dev);

@@ -242,6 +242,40 @@ def test_hash5_bit_exact_vs_oracle(ib):
     assert (got == c_oracle.hash_batch(5, raw)).all()
 
 
+def test_pageable_pinned_and_registered_host_buffers_agree(ib):
+    """Large batches from pageable memory go through the library's threaded pinned staging;
+    the same batch from inf_host_alloc'ed and from inf_host_register'ed memory is copied by
+    DMA directly.  Same outputs, ragged last chunk included, checked against the oracle."""
+    import ctypes as C
+    ctx = ib.get_context()
+    n = (1 << 20) + 3 * (1 << 18) + 12345
+    for k in (2, 5):
+        raw = random_fr_bytes(k * n, seed=40 + k, canonical=False)
+        h = ib.Poseidon.new_circom(k)
+        got = h.hash_batch(raw)                                      # pageable numpy arrays in and out
+        idx = np.r_[0:64, (1 << 18) - 32:(1 << 18) + 32, (1 << 20) - 32:(1 << 20) + 32, n - 64:n]
+        exp = c_oracle.hash_batch(k, raw.reshape(n, k * 32)[idx])
+        assert (got[idx] == exp).all()
+        if not hasattr(ctx.lib, "_name"):
+            continue
+        p_in, p_out = C.c_void_p(), C.c_void_p()
+        ctx.check(ctx.lib.inf_host_alloc(ctx.handle, raw.size, C.byref(p_in)))
+        ctx.check(ctx.lib.inf_host_alloc(ctx.handle, n * 32, C.byref(p_out)))
+        C.memmove(p_in.value, raw.ctypes.data, raw.size)
+        ctx.check(ctx.lib.inf_poseidon_hash_batch(ctx.handle, k, 0, None, p_in.value, n, p_out.value))
+        pinned = np.frombuffer(C.string_at(p_out.value, n * 32), dtype=np.uint8).reshape(n, 32)
+        assert (pinned == got).all()
+        ctx.check(ctx.lib.inf_host_free(ctx.handle, p_in))
+        ctx.check(ctx.lib.inf_host_free(ctx.handle, p_out))
+        out2 = np.empty((n, 32), dtype=np.uint8)
+        ctx.check(ctx.lib.inf_host_register(ctx.handle, raw.ctypes.data, raw.size))
+        ctx.check(ctx.lib.inf_host_register(ctx.handle, out2.ctypes.data, out2.size))
+        h.hash_batch(raw, out=out2)
+        ctx.check(ctx.lib.inf_host_unregister(ctx.handle, raw.ctypes.data))
+        ctx.check(ctx.lib.inf_host_unregister(ctx.handle, out2.ctypes.data))
+        assert (out2 == got).all()
+
+
 # ---- trees -----------------------------------------------------------------------------------
 SIZES = sorted(set(list(range(0, 41)) + [63, 64, 65, 100, 124, 125, 126, 127, 128, 129, 255, 256, 257,
                                           624, 625, 626, 1000, 1023, 1024, 1025, 3124, 3125, 3126, 5000]))
