@@ -405,6 +405,20 @@ def run_ours(args, rank, world, local_rank):
                 assert rc in (0, 2), rc
             return timed(run), root.raw.hex(), idp.value, rdp.value
 
+        # O(1) callers (commitments, the coordinator-key hash, verify_outcome): ONE hash2 — device time of the
+        # launch, the whole call from host buffers, and a second inf_init (tables cached per process, so this is
+        # uploads + the two 32-link zero chains on the device)
+        one_in = device_random_fr(2, dev, seed=1)
+        one_out = torch.empty((1, 32), dtype=torch.uint8, device=dev)
+        dev_ms = timed(lambda: h2.hash_batch_device(one_in.data_ptr(), 1, one_out.data_ptr(), stream.cuda_stream), reps=5)
+        host_in = one_in.cpu().numpy()
+        call_ms = wall(lambda: h2.hash_batch(host_in, 1), reps=5)
+        t0 = time.perf_counter()
+        ctx2 = ib.Context(dev.index or 0)
+        init_ms = (time.perf_counter() - t0) * 1e3
+        ctx2.close()
+        e2e_more["single_hash2"] = {"device_us": dev_ms * 1e3, "call_us": call_ms * 1e3, "inf_init_ms": init_ms,
+                                    "api": "inf_poseidon_hash_batch(n=1): warp-cooperative kernel"}
         # small trees: the regime the reference's dev runtime lives in (65 536 participants)
         lv = device_random_fr(1 << 16, dev, seed=16)
         ms, _, _, _ = merge_dev_ms(2, 32, lv, True, False)

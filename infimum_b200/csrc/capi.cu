@@ -649,21 +649,23 @@ int inf_init(int device, inf_ctx** out) {
     } catch (const std::exception&) {
         return fail(INF_ERR_HASH_FAILED);
     }
-    // Zero tables: Z[l+1] = H(Z[l] x arity), 32 links each, hashed on the device.
+    // Zero tables: Z[l+1] = H(Z[l] x arity), 32 links each, hashed on the device: one launch per
+    // arity (a loop over the links inside one block of the cooperative kernel), the two chains
+    // side by side on two streams.
     {
         void* d = nullptr;
-        if ((e = cudaMalloc(&d, 6 * 32)) != cudaSuccess) return fail(cuda_fail(nullptr, e, "cudaMalloc"));
-        for (int a = 0; a < 2; a++) {
-            const int arity = a == 0 ? 2 : 5;
+        if ((e = cudaMalloc(&d, 2 * 33 * 32)) != cudaSuccess) return fail(cuda_fail(nullptr, e, "cudaMalloc"));
+        cudaStream_t sts[2] = {ctx->stream, ctx->pipe[0]};
+        for (int a = 0; a < 2 && e == cudaSuccess; a++) {
+            char* da = (char*)d + a * 33 * 32;
             memcpy(ctx->zeroes[a][0], a == 0 ? host::BINARY_ZERO_LEAF_BE : host::QUINARY_ZERO_LEAF_BE, 32);
-            for (int l = 0; l < 32 && e == cudaSuccess; l++) {
-                uint8_t in[5 * 32];
-                for (int k = 0; k < arity; k++) memcpy(in + 32 * k, ctx->zeroes[a][l], 32);
-                e = cudaMemcpyAsync(d, in, arity * 32, cudaMemcpyHostToDevice, ctx->stream);
-                if (e == cudaSuccess) e = hashers[arity + 1](d, (char*)d + 5 * 32, 1, make_tag(nullptr), false, ctx->stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->zeroes[a][l + 1], (char*)d + 5 * 32, 32, cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            }
+            e = cudaMemcpyAsync(da, ctx->zeroes[a][0], 32, cudaMemcpyHostToDevice, sts[a]);
+            if (e == cudaSuccess) e = a == 0 ? launch_hash_chain_t3(da, 32, sts[a]) : launch_hash_chain_t6(da, 32, sts[a]);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->zeroes[a], da, 33 * 32, cudaMemcpyDeviceToHost, sts[a]);
+        }
+        for (int a = 0; a < 2; a++) {
+            const cudaError_t es = cudaStreamSynchronize(sts[a]);
+            if (e == cudaSuccess) e = es;
         }
         cudaFree(d);
         if (e != cudaSuccess) return fail(cuda_fail(nullptr, e, "zero-table chain"));
@@ -744,7 +746,20 @@ static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, 
     // device staging: every chunk in flight has its own region (3 streams x 2 halves)
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 6 * chunk * in_row))) return rc;
     if ((rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], 6 * chunk * 32))) return rc;
-    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    // Chunk boundaries: full chunks in the middle, smaller ones at both ends — the first upload
+    // cannot overlap with anything and neither can the last copy-out, so both are kept short.
+    std::vector<uint64_t> cut{0};
+    {
+        const uint64_t ramp[6] = {chunk / 8, chunk / 8, chunk / 8, chunk / 2, chunk / 2, chunk / 2};
+        uint64_t tail = 0;
+        for (int i = 0; i < 6; i++) tail += ramp[i];
+        uint64_t pos = 0;
+        for (int i = 0; i < 6 && pos + ramp[i] + tail < n; i++) cut.push_back(pos += ramp[i]);
+        while (pos + chunk + tail < n) cut.push_back(pos += chunk);
+        for (int i = 5; i >= 0 && pos < n; i--) cut.push_back(pos = std::min<uint64_t>(n, pos + std::max<uint64_t>(ramp[i], (n - pos) / (i + 1))));
+        if (pos < n) cut.push_back(n);
+    }
+    const uint64_t n_chunks = cut.size() - 1;
     int rcs[3] = {INF_OK, INF_OK, INF_OK};
     cudaError_t errs[3] = {cudaSuccess, cudaSuccess, cudaSuccess};
     auto worker = [&](int i) {
@@ -766,7 +781,7 @@ static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, 
         for (uint64_t k = i; k < n_chunks + 3 && e == cudaSuccess && !rcs[i]; k += 3, j++) {
             char *h_in, *h_out, *d_in, *d_out;
             if (k < n_chunks) {
-                const uint64_t off = k * chunk, c = std::min<uint64_t>(chunk, n - off);
+                const uint64_t off = cut[k], c = cut[k + 1] - off;
                 region(j & 1, &h_in, &h_out, &d_in, &d_out);
                 // this half was last used by chunk j-2, whose results were copied out in iteration j-1
                 memcpy(h_in, in + off * in_row, c * in_row);
@@ -776,7 +791,7 @@ static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, 
                 if ((e = cudaEventRecord(ctx->bounce_done[i][j & 1], st)) != cudaSuccess) break;
             }
             if (prev != UINT64_MAX) {
-                const uint64_t off = prev * chunk, c = std::min<uint64_t>(chunk, n - off);
+                const uint64_t off = cut[prev], c = cut[prev + 1] - off;
                 region((j - 1) & 1, &h_in, &h_out, &d_in, &d_out);
                 if ((e = cudaEventSynchronize(ctx->bounce_done[i][(j - 1) & 1])) != cudaSuccess) break;
                 memcpy(out + off * 32, h_out, c * 32);

@@ -67,7 +67,8 @@ struct TagArg {          // domain tag in wire order (poseidon.rs:110-120); has 
                                        uint64_t n_in, void* d_out, uint64_t n_out,                  \
                                        const uint8_t* zero_be, cudaStream_t st);                    \
     cudaError_t launch_path_root_t##N(const void* d_idx, const void* d_leaves, const void* d_paths,  \
-                                      uint32_t depth, void* d_roots, uint64_t n, cudaStream_t st);
+                                      uint32_t depth, void* d_roots, uint64_t n, cudaStream_t st);  \
+    cudaError_t launch_hash_chain_t##N(void* d_nodes, int n_links, cudaStream_t st);
 INF_DECLARE_WIDTH(2)
 INF_DECLARE_WIDTH(3)
 INF_DECLARE_WIDTH(4)

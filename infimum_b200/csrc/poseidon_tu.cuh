@@ -142,6 +142,23 @@ struct CoopBus {
     __device__ __forceinline__ void pro_wait() const { wait(BAR_PRO, 32 * T); }
 };
 
+// Role of this warp.  Blocks that share an SM all put their chain warp on the same sub-partition
+// (warps map to sub-partitions by index mod 4) and that is the better layout: chain warps are
+// latency-bound and interleave with each other almost for free, while next to the helper warps
+// of another block they are delayed by work that is never critical.  Rotating the layout by the
+// order in which blocks arrive on their SM was measured slower (8 192 parents 116 -> 127 us,
+// 16 384 parents 203 -> 232 us; profiles/r02_tree_levels.md).
+__device__ __forceinline__ int coop_role() {
+    const int w = threadIdx.x >> 5;
+    return w == COOP_CHAIN_WARP ? 0 : (w == 0 ? COOP_CHAIN_WARP : w);
+}
+
+__device__ __forceinline__ void load_node_coherent(uint32_t (&w)[8], const uint4* p) {
+    const uint4 a = __ldcg(p), b = __ldcg(p + 1);          // L2, never the non-coherent path
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+
 __global__ void __launch_bounds__(32 * COOP_WARPS, 1)
 tree_level_coop_kernel(const uint4* __restrict__ in, const uint4* __restrict__ prefix, uint64_t shift, uint64_t n_in,
                        uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
@@ -150,8 +167,7 @@ tree_level_coop_kernel(const uint4* __restrict__ in, const uint4* __restrict__ p
     extern __shared__ __align__(16) unsigned char coop_raw[];
     CoopBus bus{*reinterpret_cast<CoopSmem*>(coop_raw), (int)(threadIdx.x & 31)};
     griddep_launch_dependents();
-    const int w = threadIdx.x >> 5;
-    const int role = w == COOP_CHAIN_WARP ? 0 : (w == 0 ? COOP_CHAIN_WARP : w);
+    const int role = coop_role();
     const uint64_t h = (uint64_t)blockIdx.x * 32 + bus.lane;
     const bool live = h < n_out;          // dead lanes run along on zeros (barriers count whole warps)
     const uint32_t* tbl = c_tbl;
@@ -185,6 +201,77 @@ tree_level_coop_kernel(const uint4* __restrict__ in, const uint4* __restrict__ p
         uint32_t ow[8];
         limbs_to_words<false>(ow, hsh);
         store_node(out + 2 * h, ow);
+    }
+}
+
+// The same formulation for small batches (PoseidonHasher::hash called for a handful of
+// inputs: the commitments, the coordinator-key hash, verify_outcome): one hash costs the
+// critical path of the cooperative schedule instead of a whole single-thread hash.
+template <bool LE>
+__global__ void __launch_bounds__(32 * COOP_WARPS, 1)
+hash_batch_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_t n, TagArg tag) {
+    using L = Layout<T>;
+    constexpr int A = T - 1;
+    extern __shared__ __align__(16) unsigned char coop_raw[];
+    CoopBus bus{*reinterpret_cast<CoopSmem*>(coop_raw), (int)(threadIdx.x & 31)};
+    const int role = coop_role();
+    const uint64_t h = (uint64_t)blockIdx.x * 32 + bus.lane;
+    const bool live = h < n;
+    const uint32_t* tbl = c_tbl;
+    uint32_t s[8];
+    if (role < T && (role > 0 || tag.has)) {
+        uint32_t wd[8], raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) wd[k] = role == 0 ? tag.w[k] : 0u;
+        if (role > 0 && live) load_node(wd, in + 2 * (h * A + (role - 1)));
+        words_to_limbs<LE>(raw, wd);
+        absorb<T>(s, raw, role, tbl);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = role == 0 ? tbl[L::S0 * 8 + k] : 0u;
+    }
+    uint32_t hsh[8];
+    coop_hash<T>(hsh, s, role, bus, tbl);
+    if (role == 0 && live) {
+        uint32_t ow[8];
+        limbs_to_words<LE>(ow, hsh);
+        store_node(out + 2 * h, ow);
+    }
+}
+
+// nodes[l + 1] = H(nodes[l] x A) for l = 0 .. n_links - 1, one block: the zero tables of
+// inf_init (zeroes.rs) as ONE launch per arity instead of 32 launch + copy round trips.
+__global__ void __launch_bounds__(32 * COOP_WARPS, 1)
+hash_chain_coop_kernel(uint4* nodes, int n_links) {
+    using L = Layout<T>;
+    extern __shared__ __align__(16) unsigned char coop_raw[];
+    CoopBus bus{*reinterpret_cast<CoopSmem*>(coop_raw), (int)(threadIdx.x & 31)};
+    const int role = coop_role();
+    const uint32_t* tbl = c_tbl;
+#pragma unroll 1
+    for (int l = 0; l < n_links; l++) {
+        uint32_t s[8];
+        if (role == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = tbl[L::S0 * 8 + k];
+        } else if (role < T) {
+            uint32_t wd[8], raw[8];
+            load_node_coherent(wd, nodes + 2 * l);
+            words_to_limbs<false>(raw, wd);
+            absorb<T>(s, raw, role, tbl);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = 0;
+        }
+        uint32_t hsh[8];
+        coop_hash<T>(hsh, s, role, bus, tbl);
+        if (role == 0 && bus.lane == 0) {
+            uint32_t ow[8];
+            limbs_to_words<false>(ow, hsh);
+            store_node(nodes + 2 * (l + 1), ow);
+            __threadfence_block();
+        }
+        __syncthreads();
     }
 }
 
@@ -256,33 +343,27 @@ static int occupancy_pad() {
     return pad;
 }
 
+static unsigned sm_count() {
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return (unsigned)sms[dev];
+}
+
 // A tree level whose grid is a little more than 3 blocks per SM would run its last
 // few blocks alone, at single-warp latency, after everything else has finished; if
 // 4 or 5 blocks per SM hold the whole grid, let them (94 registers allow 5).
+// (Cutting such levels into 64-thread blocks changes nothing — 65 536 parents 509 vs 520 us:
+// what quantises a level of a few warps per sub-partition is the number of warps on the
+// fullest sub-partition, 4 against an average 3.46, and no block shape changes that.)
 static int level_pad(unsigned grid) {
-    static int sms[64] = {};
     const int pad = occupancy_pad();
     if (T > 3 || pad != 74 * 1024) return pad;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return pad;
-    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-    const unsigned n = (unsigned)sms[dev];
+    const unsigned n = sm_count();
     if (grid <= 3 * n || grid > 5 * n) return pad;
     return grid <= 4 * n ? 55 * 1024 : 44 * 1024;
-}
-
-
-cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, uint64_t n,
-                                                const TagArg& tag, bool le, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
-    const int pad = occupancy_pad();
-    if (le)
-        hash_batch_kernel<true><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
-    else
-        hash_batch_kernel<false><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
-    return cudaGetLastError();
 }
 
 // Levels with at most this many parents go to the warp-cooperative kernel: the measured
@@ -301,9 +382,42 @@ static uint64_t coop_max() {
     if (sizeof(CoopSmem) > 48 * 1024 && dev >= 0 && dev < 64 && !set_on[dev]) {
         cudaFuncSetAttribute(tree_level_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CoopSmem));
+        cudaFuncSetAttribute(hash_batch_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CoopSmem));
+        cudaFuncSetAttribute(hash_batch_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CoopSmem));
+        cudaFuncSetAttribute(hash_chain_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CoopSmem));
         set_on[dev] = true;
     }
     return (uint64_t)v;
+}
+
+cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, uint64_t n,
+                                                const TagArg& tag, bool le, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    if (n <= coop_max()) {                  // small batch: one hash costs the cooperative critical path
+        const unsigned grid = (unsigned)((n + 31) / 32);
+        if (le)
+            hash_batch_coop_kernel<true><<<grid, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        else
+            hash_batch_coop_kernel<false><<<grid, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        return cudaGetLastError();
+    }
+    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
+    const int pad = occupancy_pad();
+    if (le)
+        hash_batch_kernel<true><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+    else
+        hash_batch_kernel<false><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+    return cudaGetLastError();
+}
+
+// d_nodes[0] given; d_nodes[l + 1] = H(d_nodes[l] x (T-1)) for l < n_links, one launch.
+cudaError_t INF_CAT(launch_hash_chain_t, INF_T)(void* d_nodes, int n_links, cudaStream_t st) {
+    coop_max();
+    hash_chain_coop_kernel<<<1, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((uint4*)d_nodes, n_links);
+    return cudaGetLastError();
 }
 
 // Called by inf_init for every width on the context's device, under the init

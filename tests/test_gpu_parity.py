@@ -226,6 +226,30 @@ def test_optimised_kernel_equals_dense_kernel_on_device(ib, n_inputs):
     assert (h.hash_batch(raw) == h.hash_batch(raw, dense=True)).all()
 
 
+@pytest.mark.parametrize("n_inputs", range(1, 8))
+def test_small_and_large_batches_take_different_kernels_same_results(ib, n_inputs):
+    """Batches of at most 16 384 (widths <= 4) / 8 192 hashes run the warp-cooperative kernel (one
+    hash spread over width + 1 warps), larger ones one hash per thread: both against the oracle, at the
+    sizes where the cooperative kernel changes shape (one lane, a ragged warp, more than one block per
+    SM = rotated role layout, its largest batch), with a domain tag and in either wire order."""
+    n = 16384 + 4000
+    raw = random_fr_bytes(n_inputs * n, seed=70 + n_inputs, canonical=False).reshape(-1)
+    exp = c_oracle.hash_batch(n_inputs, raw)
+    h = ib.Poseidon.new_circom(n_inputs)
+    assert (h.hash_batch(raw) == exp).all()
+    row = n_inputs * 32
+    for m in (1, 31, 33, 4736 + 5, 8192, 8193, 16384):
+        assert (h.hash_batch(raw[: m * row]) == exp[:m]).all(), m
+    tag = 0x1234567890abcdef << 100
+    ht = ib.Poseidon.with_domain_tag_circom(n_inputs, tag)
+    rows = raw[: 40 * row].reshape(40, n_inputs, 32)
+    exp_t = np.stack([np.frombuffer(c_oracle.hash_one([bytes(x) for x in r], be(tag)), dtype=np.uint8) for r in rows])
+    assert (ht.hash_batch(raw[: 40 * row]) == exp_t).all()
+    assert (ht.hash_batch(raw[: n * row])[:40] == exp_t).all()
+    le = np.ascontiguousarray(rows[:, :, ::-1])
+    assert (ht.hash_batch(le, little_endian=True)[:, ::-1] == exp_t).all()
+
+
 def test_hash2_2_17_pairs_bit_exact_vs_oracle(ib):
     """A quick 2^17-pair batch, every output compared (the full 2^24 pairs of
     BASELINE config 2 are in tests/test_gpu_fullsize.py)."""

@@ -13,7 +13,7 @@ g = torch.Generator(device=dev); g.manual_seed(5)
 stream = torch.cuda.Stream()
 res = {}
 for arity in (2, 5):
-    sizes = [1, 32, 256, 1024, 2048, 4096, 8192, 16384, 24576, 32768, 49152, 65536, 131072, 262144]
+    sizes = [1, 32, 256, 1024, 2048, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 262144]
     for n_out in sizes:
         n_in = n_out * arity
         src = torch.randint(0, 256, (n_in, 32), dtype=torch.uint8, device=dev, generator=g)
