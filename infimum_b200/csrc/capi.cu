@@ -180,6 +180,12 @@ int check_hash_args(inf_ctx* ctx, uint32_t n_inputs, const void* in, uint64_t n,
 struct LeafFeed {
     std::function<int(uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot)> fill;
     uint64_t chunk_out = 1ull << 19;
+    // Hash level 0 chunk by chunk behind each chunk's fill (uploads of host leaves hide behind it), or
+    // only fill per chunk and hash level 0 in one launch afterwards (a feed that hashes leaves from raw
+    // rows keeps the GPU busy by itself, and level 0 in one piece runs at the full rate: the chunked
+    // form cost a replay 3 % — small level kernels, and two large kernels evicting each other's
+    // instructions; tools/replay_probe.py).
+    bool level0_per_chunk = true;
     uint8_t* leaves_out = nullptr;           // optional host copy of all leaves (n_leaves * 32 bytes)
 };
 
@@ -211,17 +217,21 @@ int reduce_levels(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_le
     uint32_t l_first = 0;
     int rc;
     if (feed) {
-        const uint64_t chunk_out = feed->chunk_out;
+        // The first chunk is a quarter and the second half the size: nothing can hide the first
+        // upload, so it is kept short.
+        static const bool ramp = !(getenv("INF_NO_RAMP") && atoi(getenv("INF_NO_RAMP")));
         int k = 0;
-        for (uint64_t o0 = 0; o0 < n1; o0 += chunk_out, k++) {
-            const uint64_t o1 = std::min<uint64_t>(o0 + chunk_out, n1);
+        for (uint64_t o0 = 0, step = 0; o0 < n1; o0 += step, k++) {
+            step = (ramp && k < 2 && feed->chunk_out >= 64) ? feed->chunk_out >> (2 - k) : feed->chunk_out;
+            const uint64_t o1 = std::min<uint64_t>(o0 + step, n1);
             const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
             const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
             cudaStream_t ps = ctx->pipe[k % 3];
             char* dl = (char*)d_in + leaf_lo * 32;
             if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return rc;
-            CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, dst_of(0) + o0 * 32, o1 - o0,
-                            Z[level_in], ps));
+            if (feed->level0_per_chunk)
+                CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, dst_of(0) + o0 * 32, o1 - o0,
+                                Z[level_in], ps));
         }
         for (int i = 0; i < 3; i++) {
             CU(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
@@ -233,10 +243,12 @@ int reduce_levels(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_le
             for (int i = 1; i < 3; i++) CU(cudaStreamWaitEvent(ctx->pipe[0], ctx->pipe_done[i], 0));
             CU(cudaMemcpyAsync(feed->leaves_out, d_in, (size_t)n_in * 32, cudaMemcpyDeviceToHost, ctx->pipe[0]));
         }
-        cur = dst_of(0);
-        n_cur = n1;
-        sh = 0;
-        l_first = 1;
+        if (feed->level0_per_chunk) {
+            cur = dst_of(0);
+            n_cur = n1;
+            sh = 0;
+            l_first = 1;
+        }
     }
     for (uint32_t l = l_first; l < n_levels; l++) {
         const uint64_t n_next = (n_cur + sh + arity - 1) / arity;
@@ -523,6 +535,7 @@ LeafFeed raw_rows_feed(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint
                        uint64_t chunk_out, size_t slot_rows, Launch launch) {
     LeafFeed f;
     f.chunk_out = chunk_out;
+    f.level0_per_chunk = false;
     f.fill = [=](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot) -> int {
         char* s0 = (char*)ctx->io[0] + (size_t)slot * slot_rows * (row0 + row1);
         char* s1 = s0 + slot_rows * row0;
@@ -1367,7 +1380,8 @@ int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint
     if (n > pow_sat(5, interaction_depth)) return INF_ERR_TREE_ALREADY_FULL;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    const uint64_t chunk_out = 1ull << 15;
+    static const int chunk_log = getenv("INF_REPLAY_CHUNK_LOG") ? atoi(getenv("INF_REPLAY_CHUNK_LOG")) : 15;
+    const uint64_t chunk_out = 1ull << chunk_log;
     const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out * 5, n + 5) + 3) & ~(size_t)3;
     int rc;
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 384))) return rc;
