@@ -179,7 +179,7 @@ int check_hash_args(inf_ctx* ctx, uint32_t n_inputs, const void* in, uint64_t n,
 // hashing) of one chunk hide behind the hashing of another.
 struct LeafFeed {
     std::function<int(uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int slot)> fill;
-    uint64_t chunk_out = 1ull << 19;
+    uint64_t chunk_out = 1ull << 19;         // parents per chunk (level0_per_chunk) or leaves per chunk (otherwise)
     // Hash level 0 chunk by chunk behind each chunk's fill (uploads of host leaves hide behind it), or
     // only fill per chunk and hash level 0 in one launch afterwards (a feed that hashes leaves from raw
     // rows keeps the GPU busy by itself, and level 0 in one piece runs at the full rate: the chunked
@@ -192,8 +192,13 @@ struct LeafFeed {
 int alloc_tree(inf_ctx* ctx, uint32_t arity, uint32_t depth, uint64_t shift, uint64_t n_leaves, inf_tree** out);
 
 // Leaves in host memory: one asynchronous upload per chunk.
+// Chunks of the host pipelines are whole waves of the wide launch shapes (one 384- or 512-thread
+// block per SM, launch.h): sms x 1536 threads = 4 waves of 384 = 3 waves of 512.
+inline uint64_t wave_unit(const inf_ctx* ctx) { return (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 1536; }
+
 LeafFeed host_leaf_feed(inf_ctx* ctx, const uint8_t* h_leaves) {
     LeafFeed f;
+    f.chunk_out = 2 * wave_unit(ctx);
     f.fill = [ctx, h_leaves](uint64_t lo, uint64_t hi, char* dst, cudaStream_t ps, int) -> int {
         CU(cudaMemcpyAsync(dst, h_leaves + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ps));
         return INF_OK;
@@ -221,17 +226,25 @@ int reduce_levels(inf_ctx* ctx, uint32_t arity, uint32_t level_in, uint32_t n_le
         // upload, so it is kept short.
         static const bool ramp = !(getenv("INF_NO_RAMP") && atoi(getenv("INF_NO_RAMP")));
         int k = 0;
-        for (uint64_t o0 = 0, step = 0; o0 < n1; o0 += step, k++) {
-            step = (ramp && k < 2 && feed->chunk_out >= 64) ? feed->chunk_out >> (2 - k) : feed->chunk_out;
-            const uint64_t o1 = std::min<uint64_t>(o0 + step, n1);
-            const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
-            const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
-            cudaStream_t ps = ctx->pipe[k % 3];
-            char* dl = (char*)d_in + leaf_lo * 32;
-            if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return rc;
-            if (feed->level0_per_chunk)
+        auto step_of = [&](int i) { return (ramp && i < 2 && feed->chunk_out >= 64) ? feed->chunk_out >> (2 - i) : feed->chunk_out; };
+        if (feed->level0_per_chunk) {
+            for (uint64_t o0 = 0, step = 0; o0 < n1; o0 += step, k++) {
+                step = step_of(k);
+                const uint64_t o1 = std::min<uint64_t>(o0 + step, n1);
+                const uint64_t L0 = o0 * arity, L1 = std::min<uint64_t>(o1 * arity, n_total);
+                const uint64_t leaf_lo = L0 >= shift ? L0 - shift : 0, leaf_hi = L1 - shift;
+                cudaStream_t ps = ctx->pipe[k % 3];
+                char* dl = (char*)d_in + leaf_lo * 32;
+                if (leaf_hi > leaf_lo && (rc = feed->fill(leaf_lo, leaf_hi, dl, ps, k % 3))) return rc;
                 CU(launch_level(arity, dl, o0 == 0 ? shift : 0, leaf_hi - leaf_lo, dst_of(0) + o0 * 32, o1 - o0,
                                 Z[level_in], ps));
+            }
+        } else {
+            for (uint64_t lo = 0; lo < n_in; k++) {
+                const uint64_t hi = std::min<uint64_t>(lo + step_of(k), n_in);
+                if ((rc = feed->fill(lo, hi, (char*)d_in + lo * 32, ctx->pipe[k % 3], k % 3))) return rc;
+                lo = hi;
+            }
         }
         for (int i = 0; i < 3; i++) {
             CU(cudaEventRecord(ctx->pipe_done[i], ctx->pipe[i]));
@@ -367,7 +380,7 @@ int tree_merge_dev(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
 template <class Launch>
 int rows_pipeline(inf_ctx* ctx, const uint8_t* in0, size_t row0, const uint8_t* in1, size_t row1,
                          uint64_t n, uint8_t* out, Launch launch) {
-    const uint64_t super = 1ull << 22, chunk = 1ull << 17;
+    const uint64_t super = 1ull << 22, chunk = wave_unit(ctx) / 2;      // two waves of the 384-thread leaf blocks
     const uint64_t n_stage = std::min<uint64_t>(n, super);
     int rc;
     // staging: io[0] holds both inputs back to back, io[1] the output
@@ -743,7 +756,7 @@ static bool is_pageable(const void* p) {
 // is already one behind.
 static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
                                const uint8_t* in, uint64_t n, uint8_t* out, bool dense, const CustomParams* custom) {
-    const uint64_t chunk = 1ull << 18;
+    const uint64_t chunk = wave_unit(ctx);
     const size_t in_row = (size_t)n_inputs * 32, slot = chunk * (in_row + 32);
     int rc;
     if (ctx->bounce_bytes < 6 * slot) {
@@ -842,7 +855,7 @@ static int hash_batch_host(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, cons
     if (n >= (1ull << 20) && (is_pageable(in) || is_pageable(out)))
         return hash_batch_pageable(ctx, n_inputs, flags, tag, in, n, out, dense, custom);
     const uint64_t super = 1ull << 24;                 // device staging is sized for at most 2^24 hashes
-    const uint64_t chunk = 1ull << 19;
+    const uint64_t chunk = 2 * wave_unit(ctx);
     const size_t in_row = (size_t)n_inputs * 32;
     const uint64_t n_stage = std::min<uint64_t>(n, super);
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], n_stage * in_row))) return rc;
@@ -1339,8 +1352,8 @@ int inf_replay_registrations(inf_ctx* ctx, uint32_t registration_depth, const ui
     if (n + 1 > pow_sat(2, registration_depth)) return INF_ERR_TREE_ALREADY_FULL;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    const uint64_t chunk_out = 1ull << 18;
-    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out * 2, n + 2) + 3) & ~(size_t)3;   // rows one pipeline stream stages at a time (keeps the slots 16-byte aligned)
+    const uint64_t chunk_out = 2 * wave_unit(ctx);     // participants per chunk: whole waves of the leaf kernel
+    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out, n + 2) + 3) & ~(size_t)3;   // rows one pipeline stream stages at a time (keeps the slots 16-byte aligned)
     int rc;
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 72))) return rc;
     if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;
@@ -1380,9 +1393,9 @@ int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint
     if (n > pow_sat(5, interaction_depth)) return INF_ERR_TREE_ALREADY_FULL;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    static const int chunk_log = getenv("INF_REPLAY_CHUNK_LOG") ? atoi(getenv("INF_REPLAY_CHUNK_LOG")) : 15;
-    const uint64_t chunk_out = 1ull << chunk_log;
-    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out * 5, n + 5) + 3) & ~(size_t)3;
+    static const int waves = getenv("INF_REPLAY_WAVES") ? atoi(getenv("INF_REPLAY_WAVES")) : 3;
+    const uint64_t chunk_out = (uint64_t)(waves > 0 ? waves : 3) * (wave_unit(ctx) / 4);   // messages per chunk: whole waves of 384-thread blocks
+    const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out, n + 5) + 3) & ~(size_t)3;
     int rc;
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 384))) return rc;
     if (!retained && (rc = grow(ctx, &ctx->io[1], &ctx->io_bytes[1], std::max<uint64_t>(n, 1) * 32))) return rc;

@@ -8,16 +8,26 @@
 #include <cstdlib>
 #include <cstring>
 
-// 128-thread blocks.  Resident blocks per SM (register cap): measured on B200
-// (tools/variant_probe.py, profiles/r01_occupancy_sweep.md) — widths 2 and 3 fit
-// 94 registers and are indifferent; from width 4 on, 4 blocks (128 registers)
-// spill and 3 blocks (168 registers) are 5-21 % faster: the multiply pipe is the
-// bottleneck, 12 warps per SM already saturate it, spills only add traffic.
+// Block shapes.  Register caps, measured on B200 (tools/variant_probe.py,
+// profiles/r01_occupancy_sweep.md): widths 2 and 3 fit 94 registers; from width 4 on, a cap
+// of 128 registers spills and 168 is 5-21 % faster — the multiply pipe is the bottleneck,
+// 12 warps per SM already saturate it, spills only add traffic.  The caps are expressed as
+// launch bounds of ONE block of 512 threads (65536 / 512 = 128 registers, widths <= 3) or 384
+// threads (170 -> 168 registers, widths >= 4) per SM, which is also the shape large launches
+// use (INF_WIDE_BLOCK): the twelve warps of a 384-thread block start together and stay
+// within a few instructions of each other, so they share the instruction stream (the round
+// loops are 37-104 KB against a ~32 KB instruction cache), where three independent 128-thread
+// blocks drift apart — measured hash5 +13.5 %, hash3 +6.5 %, hash4 +2.4 %, hash2 +0.8 %
+// (profiles/r02_lockstep_experiment.md).  Small launches (tree levels of fewer than a few
+// waves) keep 128-thread blocks, which spread over all SMs.
 #ifndef INF_BLOCK
 #define INF_BLOCK 128
 #endif
-#ifndef INF_MIN_BLOCKS
-#define INF_MIN_BLOCKS(T) ((T) >= 4 ? 3 : 4)
+#ifndef INF_MAX_BLOCK
+#define INF_MAX_BLOCK(T) ((T) >= 4 ? 384 : 512)
+#endif
+#ifndef INF_WIDE_BLOCK
+#define INF_WIDE_BLOCK 384
 #endif
 
 namespace inf {

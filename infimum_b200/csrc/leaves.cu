@@ -31,16 +31,44 @@ __device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
     p[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// Two resident blocks (255 registers): the fused kernel spills 504 bytes at the
-// 168-register cap and is 17 % slower there (measured, tools/leaf_probe.py:
-// 20.8 vs 24.4 M messages/s); at 2 blocks it runs at the sum of its parts
-// (2 x hash5 + hash4 = 41 ns per message).
-#ifndef INF_LEAF_MIN_BLOCKS
-#define INF_LEAF_MIN_BLOCKS 2
+// Launch bound: one block of 384 threads per SM (cap 168 registers, no spills), which is also
+// the shape large launches use: twelve warps that start together share the instruction stream
+// (27.2 M messages/s), three independent 128-thread blocks drift apart and thrash the
+// instruction cache (22.2 M/s); block sizes that are not a multiple of 128 leave sub-partitions
+// a warp short (320: 20.3, 352: 22.3 M/s).  A launch whose last wave of 384-thread blocks would be
+// mostly empty takes one 256-thread block per SM instead (26.9 M/s).  INF_LEAF_BLOCK forces a shape
+// (profiles/r02_lockstep_experiment.md).
+#ifndef INF_LEAF_MAX_BLOCK
+#define INF_LEAF_MAX_BLOCK 384
 #endif
+static int leaf_sms() {
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev];
+}
+static unsigned leaf_block(uint64_t n) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("INF_LEAF_BLOCK");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 128 && forced <= INF_LEAF_MAX_BLOCK && !(forced & 31)) return (unsigned)forced;
+    const uint64_t sms = (uint64_t)leaf_sms();
+    if (n < sms * 256) return 128;                   // latency regime: spread over all SMs
+    // estimated time = waves x threads per wave / measured rate (27.2, 26.9, 21.1 M messages/s)
+    auto est = [&](unsigned b, double rate) {
+        const uint64_t per_wave = sms * b;
+        return (double)((n + per_wave - 1) / per_wave) * (double)b / rate;
+    };
+    const double t384 = est(384, 27.2), t256 = est(256, 26.9), t128 = est(128, 21.1);
+    return t384 <= t256 && t384 <= t128 ? 384 : (t256 <= t128 ? 256 : 128);
+}
 
 // pk: n x (x, y) 32-byte big-endian; data: n x 10 x 32 bytes; out: n x 32 bytes
-__global__ void __launch_bounds__(INF_BLOCK, INF_LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(INF_LEAF_MAX_BLOCK, 1)
 interaction_leaf_kernel(const uint4* __restrict__ pk, const uint4* __restrict__ data,
                         uint4* __restrict__ out, uint64_t n) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,7 +92,7 @@ interaction_leaf_kernel(const uint4* __restrict__ pk, const uint4* __restrict__ 
 }
 
 // pk: n x (x, y); timestamps: n x u64 (block numbers); out: n x 32 bytes
-__global__ void __launch_bounds__(INF_BLOCK, 3)
+__global__ void __launch_bounds__(INF_LEAF_MAX_BLOCK, 1)
 registration_leaf_kernel(const uint4* __restrict__ pk, const unsigned long long* __restrict__ ts,
                          uint4* __restrict__ out, uint64_t n) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,16 +123,18 @@ cudaError_t upload_leaf_tables(const uint32_t* t5, size_t w5, const uint32_t* t6
 cudaError_t launch_interaction_leaves(const void* d_pk, const void* d_data, void* d_out, uint64_t n,
                                       cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
-    interaction_leaf_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_pk, (const uint4*)d_data, (uint4*)d_out, n);
+    const unsigned block = leaf_block(n);
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    interaction_leaf_kernel<<<grid, block, 0, st>>>((const uint4*)d_pk, (const uint4*)d_data, (uint4*)d_out, n);
     return cudaGetLastError();
 }
 
 cudaError_t launch_registration_leaves(const void* d_pk, const void* d_ts, void* d_out, uint64_t n,
                                        cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
-    registration_leaf_kernel<<<grid, INF_BLOCK, 0, st>>>((const uint4*)d_pk, (const unsigned long long*)d_ts,
+    const unsigned block = leaf_block(n);
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    registration_leaf_kernel<<<grid, block, 0, st>>>((const uint4*)d_pk, (const unsigned long long*)d_ts,
                                                        (uint4*)d_out, n);
     return cudaGetLastError();
 }

@@ -21,6 +21,15 @@
 #pragma once
 #include "fr.cuh"
 
+// Experiment (profiles/r02_lockstep_experiment.md): -DINF_LOCKSTEP puts a block barrier in every
+// iteration of the round loops so that all warps of a block fetch the same instructions at the
+// same time (the loop bodies are larger than the instruction cache).  Off in the shipped build.
+#if defined(INF_LOCKSTEP) && defined(__CUDA_ARCH__)
+#define INF_LOCKSTEP_SYNC() __syncthreads()
+#else
+#define INF_LOCKSTEP_SYNC() ((void)0)
+#endif
+
 namespace inf {
 
 // PARTIAL_ROUNDS[t-2], pallet/src/hash/parameters.rs:17-18
@@ -139,6 +148,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     for (int r = 0; r < 4; r++) {
         const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::PRE_M) * 8;
         const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::PRE_V) * 8;
+        INF_LOCKSTEP_SYNC();
 #pragma unroll
         for (int i = 0; i < T; i++) sbox(x[i], s[i]);
 #pragma unroll
@@ -161,6 +171,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         for (int j = 0; j < L::N_PAIRS; j++) {
             const uint32_t* pt = tbl + (L::PART + j * L::PAIR_STRIDE) * 8;
             uint32_t n[8];
+            INF_LOCKSTEP_SYNC();
             sbox(q[T - 1], s[0]);                                               // round A: z_a = u^5
             dot<T - 1, 8, RI>(n, &q[0][0], pt + L::P_VA * 8, pt + L::P_KA * 8);
             add8(n, n, q[T - 1]);
@@ -211,6 +222,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     for (int r = 0; r < 3; r++) {
         const uint32_t* m = tbl + (r == 0 ? L::TAIL0_M : L::FULL_M) * 8;   // s[0] still holds u: see Layout
         const uint32_t* v = tbl + (L::TAIL_V + r * T) * 8;
+        INF_LOCKSTEP_SYNC();
 #pragma unroll
         for (int i = 0; i < T; i++) sbox(x[i], s[i]);
 #pragma unroll

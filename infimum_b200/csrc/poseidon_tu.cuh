@@ -40,16 +40,22 @@ __device__ __forceinline__ void store_node(uint4* p, const uint32_t (&w)[8]) {
 }
 
 template <bool LE>
-__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
+__global__ void __launch_bounds__(INF_MAX_BLOCK(INF_T), 1)
 hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_t n, TagArg tag) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#ifdef INF_LOCKSTEP
+    const bool live = idx < n;          // every thread runs along to the barriers
+    if (!live) idx = n - 1;
+#else
+    constexpr bool live = true;
     if (idx >= n) return;
+#endif
     uint32_t iw[T - 1][8], ow[8];
     const uint4* p = in + idx * (uint64_t)(2 * (T - 1));
 #pragma unroll
     for (int i = 0; i < T - 1; i++) load_node(iw[i], p + 2 * i);
     hash_words<T, LE>(ow, iw, tag.has ? tag.w : nullptr, c_tbl);
-    store_node(out + 2 * idx, ow);
+    if (live) store_node(out + 2 * idx, ow);
 }
 
 // One level of an arity-(T-1) Merkle tree over big-endian 32-byte nodes.
@@ -61,7 +67,7 @@ hash_batch_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint64_
 // whose leaf 0 is the blank state leaf = zeroes[0] (state.rs:48-52).
 // out[i] = H(node[A*i], ..., node[A*i+A-1]); nodes past the end are the
 // level's zero value (PollStateTree::merge's right padding, state.rs:262-266).
-__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
+__global__ void __launch_bounds__(INF_MAX_BLOCK(INF_T), 1)
 tree_level_kernel(const uint4* __restrict__ in, const uint4* __restrict__ prefix, uint64_t shift, uint64_t n_in,
                   uint4* __restrict__ out, uint64_t n_out, Node32 zero) {
     constexpr int A = T - 1;
@@ -279,7 +285,7 @@ hash_chain_coop_kernel(uint4* nodes, int n_links) {
 // one path per thread.  At every level the node sits at position idx % A among
 // its A-1 siblings (which are stored in order, skipping that position), the A
 // values are hashed, idx /= A.  paths: n x depth x (A-1) x 32 bytes.
-__global__ void __launch_bounds__(INF_BLOCK, INF_MIN_BLOCKS(INF_T))
+__global__ void __launch_bounds__(INF_MAX_BLOCK(INF_T), 1)
 path_root_kernel(const uint64_t* __restrict__ indices, const uint4* __restrict__ leaves,
                  const uint4* __restrict__ paths, uint32_t depth, uint4* __restrict__ roots,
                  uint64_t n) {
@@ -333,11 +339,12 @@ static int occupancy_pad() {
     }
     int dev = 0;
     cudaGetDevice(&dev);
-    if (pad > 48 * 1024 && dev >= 0 && dev < 64 && !set_on[dev]) {
-        cudaFuncSetAttribute(hash_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        cudaFuncSetAttribute(hash_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        cudaFuncSetAttribute(path_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    if (dev >= 0 && dev < 64 && !set_on[dev]) {
+        const int most = 200 * 1024;      // any pad the geometry helpers may ask for
+        cudaFuncSetAttribute(hash_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        cudaFuncSetAttribute(hash_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        cudaFuncSetAttribute(path_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         set_on[dev] = true;
     }
     return pad;
@@ -350,6 +357,51 @@ static unsigned sm_count() {
     if (dev < 0 || dev >= 64) return 148;
     if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
     return (unsigned)sms[dev];
+}
+
+// Block shape of a launch of n threads.  Wide blocks run one per SM, so a launch takes a whole
+// number of waves of sms x block threads, at a rate that depends on the shape (measured,
+// profiles/r02_lockstep_experiment.md, relative to one 384-thread block per SM):
+//   widths <= 3:  512 threads 0.996, three 128-thread blocks 0.985 (256 x 1 does not saturate the pipe)
+//   widths >= 4:  256 threads 0.958, three 128-thread blocks 0.935
+// The shape with the smallest estimated time (waves x threads per wave / rate) is taken; launches
+// of less than one wave of 384 keep 128-thread blocks, which spread over all SMs (latency regime).
+// INF_WIDE_BLOCK=128 gives the round-1 geometry everywhere, 256 / 384 / 512 force one shape.
+struct Geom {
+    unsigned block;
+    int pad;
+    bool wide;
+};
+static Geom pick_geom(uint64_t n) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("INF_WIDE_BLOCK");
+        forced = e ? atoi(e) : -1;
+        if (forced > INF_MAX_BLOCK(T)) forced = INF_MAX_BLOCK(T);
+    }
+    const uint64_t sms = sm_count();
+    unsigned best = 128;
+    if (forced == 256 || forced == 384 || forced == 512) {
+        best = (unsigned)forced;
+    } else if (forced != 128 && n >= sms * 384) {
+        auto est = [&](unsigned b, double rate) {
+            const uint64_t per_wave = sms * b;
+            return (double)((n + per_wave - 1) / per_wave) * (double)b / rate;
+        };
+        double tb = est(128, T <= 3 ? 0.985 : 0.935);
+        const unsigned shapes[3] = {384, 512, 256};
+        const double rates[3] = {1.0, 0.996, T <= 3 ? 0.0 : 0.958};
+        for (int i = 0; i < 3; i++) {
+            if (shapes[i] > (unsigned)INF_MAX_BLOCK(T) || rates[i] <= 0.0) continue;
+            const double t = est(shapes[i], rates[i]);
+            if (t < tb) {
+                tb = t;
+                best = shapes[i];
+            }
+        }
+    }
+    if (best == 128) return {INF_BLOCK, occupancy_pad(), false};
+    return {best, best == 256 ? 120 * 1024 : 0, true};
 }
 
 // A tree level whose grid is a little more than 3 blocks per SM would run its last
@@ -404,12 +456,12 @@ cudaError_t INF_CAT(launch_hash_batch_t, INF_T)(const void* d_in, void* d_out, u
             hash_batch_coop_kernel<false><<<grid, 32 * COOP_WARPS, sizeof(CoopSmem), st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
         return cudaGetLastError();
     }
-    const unsigned grid = (unsigned)((n + INF_BLOCK - 1) / INF_BLOCK);
-    const int pad = occupancy_pad();
+    const Geom g = pick_geom(n);
+    const unsigned grid = (unsigned)((n + g.block - 1) / g.block);
     if (le)
-        hash_batch_kernel<true><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        hash_batch_kernel<true><<<grid, g.block, g.pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
     else
-        hash_batch_kernel<false><<<grid, INF_BLOCK, pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
+        hash_batch_kernel<false><<<grid, g.block, g.pad, st>>>((const uint4*)d_in, (uint4*)d_out, n, tag);
     return cudaGetLastError();
 }
 
@@ -442,6 +494,10 @@ cudaError_t INF_CAT(launch_tree_level_t, INF_T)(const void* d_in, const void* d_
                               (const uint4*)d_in,
                               (const uint4*)d_prefix, shift, n_in, (uint4*)d_out, n_out, z);
     }
+    const Geom g = pick_geom(n_out);
+    if (g.wide)
+        return launch_chained(tree_level_kernel, (unsigned)((n_out + g.block - 1) / g.block), g.block, g.pad, st, false,
+                              (const uint4*)d_in, (const uint4*)d_prefix, shift, n_in, (uint4*)d_out, n_out, z);
     const unsigned grid = (unsigned)((n_out + INF_BLOCK - 1) / INF_BLOCK);
     return launch_chained(tree_level_kernel, grid, INF_BLOCK, level_pad(grid), st, false, (const uint4*)d_in,
                           (const uint4*)d_prefix, shift, n_in, (uint4*)d_out, n_out, z);
