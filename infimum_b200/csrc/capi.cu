@@ -1393,8 +1393,8 @@ int inf_replay_interactions(inf_ctx* ctx, uint32_t interaction_depth, const uint
     if (n > pow_sat(5, interaction_depth)) return INF_ERR_TREE_ALREADY_FULL;
     Bind bind(ctx);
     if (!bind.ok) return INF_ERR_NO_DEVICE;
-    static const int waves = getenv("INF_REPLAY_WAVES") ? atoi(getenv("INF_REPLAY_WAVES")) : 3;
-    const uint64_t chunk_out = (uint64_t)(waves > 0 ? waves : 3) * (wave_unit(ctx) / 4);   // messages per chunk: whole waves of 384-thread blocks
+    static const int waves = getenv("INF_REPLAY_WAVES") ? atoi(getenv("INF_REPLAY_WAVES")) : 4;
+    const uint64_t chunk_out = (uint64_t)(waves > 0 ? waves : 4) * (wave_unit(ctx) / 4);   // messages per chunk: whole waves of 384-thread blocks
     const size_t slot_rows = ((size_t)std::min<uint64_t>(chunk_out, n + 5) + 3) & ~(size_t)3;
     int rc;
     if ((rc = grow(ctx, &ctx->io[0], &ctx->io_bytes[0], 3 * slot_rows * 384))) return rc;

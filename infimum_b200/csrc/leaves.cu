@@ -63,7 +63,7 @@ static unsigned leaf_block(uint64_t n) {
         const uint64_t per_wave = sms * b;
         return (double)((n + per_wave - 1) / per_wave) * (double)b / rate;
     };
-    const double t384 = est(384, 27.2), t256 = est(256, 26.9), t128 = est(128, 21.1);
+    const double t384 = 0.99 * est(384, 27.2), t256 = est(256, 26.9), t128 = est(128, 21.1);   // ties go to 384
     return t384 <= t256 && t384 <= t128 ? 384 : (t256 <= t128 ? 256 : 128);
 }
 
