@@ -323,16 +323,21 @@ inline std::array<HashBytes, 5> empty_ballot_roots() {                          
 }
 
 // ---- PollStateTree ------------------------------------------------------------------------------
-// Same fields as the reference struct (state.rs:70-91).  The reference hashes
-// inside insert() and keeps only the frontier; here insert() buffers the leaf
-// and the device does all the hashing in merge() (or when the last insert
-// completes the tree).  `hashes` is materialised on request by frontier().
+// Same fields as the reference struct (state.rs:70-91).  What has been hashed in so far is
+// held the way the pallet stores it — the frontier `hashes` — plus a buffer of leaves not yet
+// folded in, so a tree can be resumed from persisted state (from_state; what the pallet reads
+// back from storage, lib.rs:706-714) and never needs its leaf history.  The reference hashes
+// inside insert(); here insert() buffers the leaf and the device folds the whole buffer into
+// the frontier in one go (inf_tree_append) when frontier() asks for it, when the last insert
+// completes the tree, or in merge().  A tree that still is what new_() made is reduced by
+// merge() in one shot (inf_tree_merge), any other from its frontier (inf_tree_merge_frontier).
+// `hashes` is current after frontier(), merge() or a completing insert.
 struct PollStateTree {
     uint8_t depth = 0;
     uint8_t full_depth = 0;
     uint8_t arity = 0;
     uint32_t count = 0;
-    std::vector<std::pair<uint8_t, HashBytes>> hashes;    // filled by frontier(); empty once merged
+    std::vector<std::pair<uint8_t, HashBytes>> hashes;    // the stored frontier; empty once merged
     std::optional<HashBytes> root;
 
     static PollStateTree new_(uint8_t arity, uint8_t full_depth,
@@ -341,12 +346,29 @@ struct PollStateTree {
         t.arity = arity;
         t.full_depth = full_depth;
         t.ctx_ = ctx ? ctx : &Context::global();
-        if (zero_hash) {
-            // the pallet only ever seeds (0, zeroes[0]) (state.rs:48-52)
-            if (zero_hash->first != 0 || zero_hash->second != get_merkle_zeroes(arity, t.ctx_)[0])
-                throw std::invalid_argument("only the reference's seeding (level 0, zeroes[0]) is supported");
-            t.seeded_ = true;
+        if (zero_hash) {                                                   // state.rs:150-158
+            t.hashes.push_back(*zero_hash);
+            // the pallet only ever seeds (0, zeroes[0]) (state.rs:48-52): that case has the one-shot merge
+            t.blank_ = zero_hash->first == 0 && zero_hash->second == get_merkle_zeroes(arity, t.ctx_)[0];
+            t.fresh_ = t.blank_;
         }
+        return t;
+    }
+
+    // Resume from the persisted struct: insert / merge continue from the stored frontier.
+    static PollStateTree from_state(uint8_t arity, uint8_t full_depth, uint8_t depth, uint32_t count,
+                                    std::vector<std::pair<uint8_t, HashBytes>> hashes, std::optional<HashBytes> root,
+                                    Context* ctx = nullptr) {
+        PollStateTree t;
+        t.arity = arity;
+        t.full_depth = full_depth;
+        t.depth = depth;
+        t.count = count;
+        t.hashes = std::move(hashes);
+        t.root = root;
+        t.ctx_ = ctx ? ctx : &Context::global();
+        t.fresh_ = false;
+        t.depth_flushed_ = depth;
         return t;
     }
 
@@ -358,21 +380,40 @@ struct PollStateTree {
         if (root) return MerkleTreeError::TreeAlreadyFull;                 // state.rs:182
         const unsigned __int128 cap = capacity();
         if ((unsigned __int128)total() + n > cap) return MerkleTreeError::TreeAlreadyFull;
+        if (pending() == 0) depth_flushed_ = depth;
         leaves_.insert(leaves_.end(), leaves, leaves + 32 * n);
         count += (uint32_t)n;
         uint8_t d = 0;
         while (d < full_depth && ipow(d + 1) <= total()) d++;
-        depth = d;                                                         // state.rs:212-213
+        if (d > depth) depth = d;                                          // state.rs:212-213
         if ((unsigned __int128)total() == cap) {                           // state.rs:218-222
-            int rc = run_merge(true);
+            int rc = fresh_ ? run_merge(true) : flush();
             if (rc != INF_OK && rc != INF_ERR_TREE_ALREADY_MERGED) return tree_error(rc);
         }
         return std::move(*this);
     }
     Result<PollStateTree, MerkleTreeError> merge(bool to_depth) && {       // state.rs:230-281
         if (root) return MerkleTreeError::TreeAlreadyMerged;
-        int rc = run_merge(to_depth);
-        if (rc != INF_OK) return tree_error(rc);
+        if (fresh_) {
+            int rc = run_merge(to_depth);
+            if (rc != INF_OK) return tree_error(rc);
+            return std::move(*this);
+        }
+        int rc = flush();
+        if (rc != INF_OK && rc != INF_ERR_TREE_ALREADY_MERGED) return tree_error(rc);
+        if (root) return std::move(*this);
+        std::vector<uint8_t> lv, hs;
+        pack(lv, hs);
+        HashBytes r;
+        int has = 0;
+        uint32_t rdepth = 0;
+        rc = inf_tree_merge_frontier(ctx_->get(), arity, full_depth, lv.data(), hs.data(), (uint32_t)lv.size(), to_depth,
+                                     r.data(), &has, &rdepth);
+        if (rc) return tree_error(rc);
+        if (has) {
+            root = r;
+            hashes.clear();
+        }
         return std::move(*this);
     }
     // state.rs:284-302
@@ -383,31 +424,26 @@ struct PollStateTree {
         for (const HashBytes& b : inputs) s.push_back({b.data(), b.size()});
         return h.unwrap().hash_bytes_be(s);
     }
-    // Materialise `hashes` (the reference's persisted frontier) for the leaves inserted so far.
+    // Bring `hashes` (the reference's persisted frontier) up to date with every leaf inserted so far.
     Result<PollStateTree, MerkleTreeError> frontier() && {
-        hashes.clear();
-        if (root) return std::move(*this);
-        uint8_t levels[4 * 33];
-        std::vector<uint8_t> hs(4 * 33 * 32);
-        uint32_t n = 0, idepth = 0;
-        int has = 0;
-        HashBytes r;
-        int rc = inf_tree_frontier(ctx_->get(), arity, full_depth, seeded_, leaves_.data(), count, levels, hs.data(),
-                                   4 * 33, &n, &idepth, &has, r.data());
-        if (rc) return tree_error(rc);
-        for (uint32_t i = 0; i < n; i++) {
-            HashBytes h;
-            memcpy(h.data(), &hs[32 * i], 32);
-            hashes.push_back({levels[i], h});
-        }
+        int rc = flush();
+        if (rc != INF_OK && rc != INF_ERR_TREE_ALREADY_MERGED) return tree_error(rc);
         return std::move(*this);
     }
 
 private:
     Context* ctx_ = nullptr;
-    bool seeded_ = false;
-    std::vector<uint8_t> leaves_;
-    uint64_t total() const { return (uint64_t)count + (seeded_ ? 1 : 0); }
+    bool blank_ = false;              // seeded with the reference's blank leaf (0, zeroes[0])
+    bool fresh_ = true;               // the frontier is still what new_() made: one-shot merge applies
+    uint8_t depth_flushed_ = 0;       // `depth` as of the stored frontier (before the buffered leaves)
+    std::vector<uint8_t> leaves_;     // leaves not yet folded into `hashes`
+    uint64_t pending() const { return leaves_.size() / 32; }
+    uint64_t logical() const {        // leaves the frontier stands for (the blank leaf included)
+        unsigned __int128 n = 0;
+        for (const auto& e : hashes) n += ipow(e.first);
+        return n > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)n;
+    }
+    uint64_t total() const { return logical() + pending(); }
     unsigned __int128 capacity() const {
         unsigned __int128 c = 1;
         for (int i = 0; i < full_depth; i++) c *= arity;
@@ -421,11 +457,45 @@ private:
     static MerkleTreeError tree_error(int rc) {
         return (rc >= 1 && rc <= 4) ? static_cast<MerkleTreeError>(rc) : MerkleTreeError::HashFailed;
     }
+    void pack(std::vector<uint8_t>& lv, std::vector<uint8_t>& hs) const {
+        for (const auto& e : hashes) {
+            lv.push_back(e.first);
+            hs.insert(hs.end(), e.second.begin(), e.second.end());
+        }
+    }
+    // Fold the buffered leaves into the frontier: insert() x pending on the stored state.
+    int flush() {
+        if (pending() == 0 || root) return INF_OK;
+        std::vector<uint8_t> lv, hs;
+        pack(lv, hs);
+        uint8_t out_lv[4 * 33];
+        std::vector<uint8_t> out_hs(4 * 33 * 32);
+        uint32_t n = 0, d = 0;
+        int has = 0;
+        HashBytes r;
+        int rc = inf_tree_append(ctx_->get(), arity, full_depth, lv.data(), hs.data(), (uint32_t)lv.size(), depth_flushed_,
+                                 leaves_.data(), pending(), out_lv, out_hs.data(), 4 * 33, &n, &d, &has, r.data());
+        if (rc != INF_OK && rc != INF_ERR_TREE_ALREADY_MERGED) return rc;
+        hashes.clear();
+        for (uint32_t i = 0; i < n; i++) {
+            HashBytes h;
+            memcpy(h.data(), &out_hs[32 * i], 32);
+            hashes.push_back({out_lv[i], h});
+        }
+        leaves_.clear();
+        leaves_.shrink_to_fit();
+        fresh_ = false;
+        depth = (uint8_t)d;
+        depth_flushed_ = depth;
+        if (has) root = r;
+        return rc;
+    }
+    // One-shot new + insert x N + merge over the buffered leaves (fresh trees only).
     int run_merge(bool to_depth) {
         HashBytes r;
         uint32_t idepth = 0, rdepth = 0;
         int has = 0;
-        int rc = inf_tree_merge(ctx_->get(), arity, full_depth, seeded_, to_depth, leaves_.data(), count, r.data(),
+        int rc = inf_tree_merge(ctx_->get(), arity, full_depth, blank_, to_depth, leaves_.data(), pending(), r.data(),
                                 &idepth, &rdepth, &has);
         if (rc == INF_OK || rc == INF_ERR_TREE_ALREADY_MERGED) {
             if (has) {

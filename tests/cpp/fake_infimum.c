@@ -225,7 +225,54 @@ int inf_tree_merge(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank,
     return rc;
 }
 
-/* the insert cascade of state.rs:176-225, literally */
+/* the insert cascade of state.rs:176-225, literally, on a stack that may start from a stored frontier */
+typedef struct {
+    uint8_t lv[5 * 34];
+    uint8_t hs[5 * 34][32];
+    int top;
+    uint32_t depth;
+    int done;
+} cascade;
+
+static void cascade_push(cascade* c, uint32_t arity, uint32_t full_depth, const uint8_t* leaf) {
+    c->lv[c->top] = 0;
+    memcpy(c->hs[c->top], leaf, 32);
+    c->top++;
+    while (c->top >= (int)arity) {
+        int same = 1;
+        for (uint32_t k = 1; k < arity; k++) same &= c->lv[c->top - 1 - k] == c->lv[c->top - 1];
+        if (!same) break;
+        uint8_t in[5 * 32], h[32];
+        for (uint32_t k = 0; k < arity; k++) memcpy(in + 32 * k, c->hs[c->top - arity + k], 32);
+        oracle_hash((int)arity, in, NULL, h, 0);
+        const uint8_t d = (uint8_t)(c->lv[c->top - 1] + 1);
+        c->top -= (int)arity;
+        c->lv[c->top] = d;
+        memcpy(c->hs[c->top], h, 32);
+        c->top++;
+        if (d > c->depth) c->depth = d;
+    }
+    if (c->top == 1 && c->lv[0] == full_depth) c->done = 1;
+}
+
+static int cascade_out(const cascade* c, uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
+                       uint32_t* depth_out, int* has_root, uint8_t root[32]) {
+    if (depth_out) *depth_out = c->depth;
+    if (c->done) {
+        if (has_root) *has_root = 1;
+        if (root) memcpy(root, c->hs[0], 32);
+        return INF_OK;
+    }
+    if ((uint32_t)c->top > cap) return INF_ERR_BUFFER_TOO_SMALL;
+    if (c->top && (!out_levels || !out_hashes)) return INF_ERR_NULL_POINTER;
+    for (int i = 0; i < c->top; i++) {
+        out_levels[i] = c->lv[i];
+        memcpy(out_hashes + 32 * i, c->hs[i], 32);
+    }
+    *n_entries = (uint32_t)c->top;
+    return INF_OK;
+}
+
 int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int blank, const uint8_t* leaves, uint64_t n,
                       uint8_t* out_levels, uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries,
                       uint32_t* insert_depth, int* has_root, uint8_t root[32]) {
@@ -238,43 +285,72 @@ int inf_tree_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, int bla
     if (total > ipow(arity, full_depth)) return INF_ERR_TREE_ALREADY_FULL;
     uint8_t z[33][32];
     zero_table(arity, z);
-    uint8_t lv[5 * 34];
-    uint8_t hs[5 * 34][32];
+    cascade c;
+    memset(&c, 0, sizeof c);
+    if (blank) cascade_push(&c, arity, full_depth, z[0]);
+    for (uint64_t i = 0; i < n; i++) cascade_push(&c, arity, full_depth, leaves + 32 * i);
+    return cascade_out(&c, out_levels, out_hashes, cap, n_entries, insert_depth, has_root, root);
+}
+
+/* insert() x n on a stored frontier (include/infimum_b200.h: inf_tree_append) */
+int inf_tree_append(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* in_levels, const uint8_t* in_hashes,
+                    uint32_t n_in, uint32_t depth_in, const uint8_t* leaves, uint64_t n, uint8_t* out_levels,
+                    uint8_t* out_hashes, uint32_t cap, uint32_t* n_entries, uint32_t* depth_out, int* has_root,
+                    uint8_t root[32]) {
+    if (!ctx || !n_entries) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    *n_entries = 0;
+    if (has_root) *has_root = 0;
+    cascade c;
+    memset(&c, 0, sizeof c);
+    c.depth = depth_in;
+    uint64_t logical = 0;
+    for (uint32_t i = 0; i < n_in; i++) {
+        if (in_levels[i] >= full_depth || (i && in_levels[i] > in_levels[i - 1])) return INF_ERR_BAD_FRONTIER;
+        c.lv[c.top] = in_levels[i];
+        memcpy(c.hs[c.top], in_hashes + 32 * i, 32);
+        c.top++;
+        logical += ipow(arity, in_levels[i]);
+    }
+    if (logical + n > ipow(arity, full_depth)) return INF_ERR_TREE_ALREADY_FULL;
+    for (uint64_t i = 0; i < n; i++) cascade_push(&c, arity, full_depth, leaves + 32 * i);
+    return cascade_out(&c, out_levels, out_hashes, cap, n_entries, depth_out, has_root, root);
+}
+
+/* merge(to_depth) on a stored frontier, state.rs:230-281 */
+int inf_tree_merge_frontier(inf_ctx* ctx, uint32_t arity, uint32_t full_depth, const uint8_t* levels, const uint8_t* hashes,
+                            uint32_t n, int to_depth, uint8_t root[32], int* has_root, uint32_t* root_depth) {
+    if (!ctx) return INF_ERR_NULL_POINTER;
+    if (arity != 2 && arity != 5) return INF_ERR_BAD_ARITY;
+    if (has_root) *has_root = 0;
+    if (root_depth) *root_depth = 0;
+    if (n == 0) return INF_OK;
+    uint8_t z[33][32];
+    zero_table(arity, z);
+    uint8_t lv[5 * 34], hs[5 * 34][32];
     int top = 0;
-    uint32_t depth = 0;
-    int done = 0;
-    for (uint64_t i = 0; i < total; i++) {
-        lv[top] = 0;
-        memcpy(hs[top], (blank && i == 0) ? z[0] : leaves + (i - (blank ? 1 : 0)) * 32, 32);
+    for (uint32_t i = 0; i < n; i++) {
+        lv[top] = levels[i];
+        memcpy(hs[top], hashes + 32 * i, 32);
         top++;
-        while (top >= (int)arity) {
-            int same = 1;
-            for (uint32_t k = 1; k < arity; k++) same &= lv[top - 1 - k] == lv[top - 1];
-            if (!same) break;
-            uint8_t in[5 * 32], h[32];
-            for (uint32_t k = 0; k < arity; k++) memcpy(in + 32 * k, hs[top - arity + k], 32);
-            oracle_hash((int)arity, in, NULL, h, 0);
-            const uint8_t d = (uint8_t)(lv[top - 1] + 1);
-            top -= (int)arity;
-            lv[top] = d;
-            memcpy(hs[top], h, 32);
-            top++;
-            if (d > depth) depth = d;
-        }
-        if (top == 1 && lv[0] == full_depth) done = 1;
     }
-    if (insert_depth) *insert_depth = depth;
-    if (done) {
-        if (has_root) *has_root = 1;
-        if (root) memcpy(root, hs[0], 32);
-        return INF_OK;
+    for (;;) {
+        const uint8_t d = lv[top - 1];
+        if (top == 1 && (!to_depth || d == full_depth)) break;
+        int run = 0;
+        while (run < top && lv[top - 1 - run] == d) run++;
+        uint8_t in[5 * 32], h[32];
+        for (int k = 0; k < run; k++) memcpy(in + 32 * k, hs[top - run + k], 32);
+        for (uint32_t k = (uint32_t)run; k < arity; k++) memcpy(in + 32 * k, z[d], 32);
+        oracle_hash((int)arity, in, NULL, h, 0);
+        top -= run;
+        lv[top] = (uint8_t)(d + 1);
+        memcpy(hs[top], h, 32);
+        top++;
     }
-    if ((uint32_t)top > cap || (top && (!out_levels || !out_hashes))) return INF_ERR_NULL_POINTER;
-    for (int i = 0; i < top; i++) {
-        out_levels[i] = lv[i];
-        memcpy(out_hashes + 32 * i, hs[i], 32);
-    }
-    *n_entries = (uint32_t)top;
+    if (root) memcpy(root, hs[0], 32);
+    if (has_root) *has_root = 1;
+    if (root_depth) *root_depth = lv[0];
     return INF_OK;
 }
 

@@ -257,6 +257,55 @@ static void tree_and_frontier_vs_oracle() {
     }
 }
 
+// ---- the stored tree: persist {depth, count, hashes, root}, resume, insert more, merge ---------------
+// (what every extrinsic does through storage, lib.rs:706-714; state.rs:176-225, 230-281)
+static void insert_and_merge_on_a_stored_frontier() {
+    std::mt19937_64 rng(0x46524F4E54);
+    for (auto [arity, full_depth, blank, to_depth] : {std::tuple<int, int, bool, bool>{2, 11, true, false}, {5, 5, false, true},
+                                                     {2, 11, false, true}, {5, 5, true, false}}) {
+        const uint64_t cap = (uint64_t)std::pow(arity, full_depth);
+        for (uint64_t n : {1ull, 2ull, 5ull, 26ull, 127ull, 700ull, 2046ull}) {
+            if (n + blank > cap) continue;
+            std::vector<uint8_t> leaves(32 * n);
+            for (auto& b : leaves) b = (uint8_t)rng();
+            uint8_t exp[32];
+            uint32_t st[3];
+            int rc = oracle_tree_insert_merge(arity, full_depth, blank, to_depth, leaves.data(), n, exp, st, 0);
+            CHECK(rc == 0);
+            auto zero = blank ? std::optional(std::make_pair((uint8_t)0, get_merkle_zeroes(arity)[0])) : std::nullopt;
+            for (uint64_t k : {(uint64_t)0, n / 3, n / 2, n - 1, n}) {
+                // first session: k leaves, state brought up to date and "persisted"
+                PollStateTree a = PollStateTree::new_(arity, full_depth, zero);
+                a = std::move(a).extend(leaves.data(), k).unwrap();
+                a = std::move(a).frontier().unwrap();
+                // second session: resumed from the stored fields only
+                PollStateTree b = PollStateTree::from_state(a.arity, a.full_depth, a.depth, a.count, a.hashes, a.root);
+                if (b.root) {                      // the first k leaves already completed the tree
+                    CHECK(k + blank == cap);
+                    continue;
+                }
+                b = std::move(b).extend(leaves.data() + 32 * k, n - k).unwrap();
+                CHECK(b.count == st[1]);
+                if (!b.root) b = std::move(b).merge(to_depth).unwrap();
+                CHECK(b.depth == st[0]);
+                if (st[2]) CHECK(b.root == std::optional<HashBytes>(HB(exp)));
+                CHECK(b.hashes.empty() == b.root.has_value());
+            }
+        }
+    }
+    // a resumed tree that is full rejects the next leaf, a merged one rejects merge (state.rs:178-182, 236)
+    PollStateTree t = new_registration_tree(2);
+    t = std::move(t).extend(be32(1).data(), 1).unwrap();
+    t = std::move(t).frontier().unwrap();
+    PollStateTree r = PollStateTree::from_state(t.arity, t.full_depth, t.depth, t.count, t.hashes, t.root);
+    std::vector<uint8_t> two(64, 7);
+    r = std::move(r).extend(two.data(), 2).unwrap();                 // blank + 3 = 4 = 2^2: completed by insert
+    CHECK(r.root.has_value() && r.hashes.empty() && r.depth == 2);
+    PollStateTree c = r;
+    CHECK(std::move(c).merge(false).unwrap_err() == MerkleTreeError::TreeAlreadyMerged);
+    CHECK(to_u8(std::move(r).insert(be32(9)).unwrap_err()) == 1);
+}
+
 // ---- leaf hashing through the Poll mirror (provider.rs:218-287) -----------------------------------
 static void poll_register_interact_merge() {
     Poll poll(G_REGISTRATION_DEPTH, G_INTERACTION_DEPTH, G_PROCESS_SUBTREE_DEPTH, G_TALLY_SUBTREE_DEPTH);
@@ -339,6 +388,7 @@ int main() {
         {"process_messages_public_signals", process_messages_public_signals},
         {"participant_limit_reached", participant_limit_reached},
         {"tree_and_frontier_vs_oracle", tree_and_frontier_vs_oracle},
+        {"insert_and_merge_on_a_stored_frontier", insert_and_merge_on_a_stored_frontier},
         {"poll_register_interact_merge", poll_register_interact_merge},
         {"verify_outcome_scenarios", verify_outcome_scenarios},
         {"retained_tree_paths", retained_tree_paths},
