@@ -115,6 +115,8 @@ registration_leaf_kernel(const uint4* __restrict__ pk, const unsigned long long*
 
 cudaError_t upload_leaf_tables(const uint32_t* t5, size_t w5, const uint32_t* t6, size_t w6) {
     if (w5 != (size_t)Layout<5>::WORDS || w6 != (size_t)Layout<6>::WORDS) return cudaErrorInvalidValue;
+    leaf_block(1);          // settle the lazily read overrides and the per-device SM count here, under inf_init's lock
+    leaf_sms();
     cudaError_t e = cudaMemcpyToSymbol(c_tbl5, t5, w5 * 4);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_tbl6, t6, w6 * 4);

@@ -479,6 +479,8 @@ cudaError_t INF_CAT(upload_table_t, INF_T)(const uint32_t* host_tbl, size_t word
     if (words != (size_t)Layout<T>::WORDS) return cudaErrorInvalidValue;
     occupancy_pad();
     coop_max();
+    sm_count();
+    pick_geom(1);
     return cudaMemcpyToSymbol(c_tbl, host_tbl, words * sizeof(uint32_t));
 }
 

@@ -250,6 +250,37 @@ def test_small_and_large_batches_take_different_kernels_same_results(ib, n_input
     assert (ht.hash_batch(le, little_endian=True)[:, ::-1] == exp_t).all()
 
 
+@pytest.mark.parametrize("n_inputs", [2, 5])
+def test_batches_at_wave_boundaries_of_the_wide_launch_shapes(ib, n_inputs):
+    """Large launches run one 256-, 384- or 512-thread block per SM, chosen per launch; sizes just below, at
+    and just above whole waves of every shape (the ragged last block must neither drop nor invent a hash)."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    sizes = sorted({sms * b * w + d for b in (256, 384, 512) for w in (1, 2) for d in (-1, 0, 1)})
+    row = n_inputs * 32
+    raw = random_fr_bytes(n_inputs * sizes[-1], seed=90 + n_inputs).reshape(-1)
+    exp = c_oracle.hash_batch(n_inputs, raw)
+    h = ib.Poseidon.new_circom(n_inputs)
+    for n in sizes:
+        out = np.full((n + 1, 32), 0xA5, dtype=np.uint8)
+        h.hash_batch(raw[: n * row], n, out=out[:n])
+        assert (out[:n] == exp[:n]).all(), n
+        assert (out[n] == 0xA5).all(), n
+
+
+@pytest.mark.parametrize("arity,depth", [(2, 18), (5, 8)])
+def test_tree_levels_at_wave_boundaries(ib, arity, depth):
+    """The same for tree levels: level 0 one parent more than a whole wave of 384-thread blocks (ragged last
+    group included), the levels above at whatever shape their size picks."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n in (arity * sms * 384 + 1, arity * sms * 512 - 1):
+        leaves = random_fr_bytes(n, seed=n % 1000)
+        t = ib.PollStateTree.new(arity, depth).extend(leaves).merge(True)
+        rc, root, d, c = c_oracle.tree_insert_merge(arity, depth, False, True, leaves)
+        assert rc == 0 and t.root == root and t.depth == d, (arity, n)
+
+
 def test_hash2_2_17_pairs_bit_exact_vs_oracle(ib):
     """A quick 2^17-pair batch, every output compared (the full 2^24 pairs of
     BASELINE config 2 are in tests/test_gpu_fullsize.py)."""
