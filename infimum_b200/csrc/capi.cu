@@ -756,8 +756,12 @@ static bool is_pageable(const void* p) {
 // is already one behind.
 static int hash_batch_pageable(inf_ctx* ctx, uint32_t n_inputs, uint32_t flags, const uint8_t* tag,
                                const uint8_t* in, uint64_t n, uint8_t* out, bool dense, const CustomParams* custom) {
-    const uint64_t chunk = wave_unit(ctx);
-    const size_t in_row = (size_t)n_inputs * 32, slot = chunk * (in_row + 32);
+    // whole waves of 384-thread blocks, at most four, and at most ~24 MB of pinned staging per slot
+    // (six slots: wide inputs would otherwise pin half a gigabyte)
+    const size_t in_row = (size_t)n_inputs * 32;
+    const uint64_t per_wave = wave_unit(ctx) / 4;
+    const uint64_t chunk = per_wave * std::max<uint64_t>(1, std::min<uint64_t>(4, (24ull << 20) / ((in_row + 32) * per_wave)));
+    const size_t slot = chunk * (in_row + 32);
     int rc;
     if (ctx->bounce_bytes < 6 * slot) {
         if (ctx->bounce) CU(cudaFreeHost(ctx->bounce));
