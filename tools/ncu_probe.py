@@ -35,6 +35,15 @@ def level(arity, n_out):
     assert rc == 0 and got.value == n_out
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "headline":
+    # the bench's timed launch itself: 2^24 hash2 (roofline.traffic = its DRAM bytes, profiles/r02_hash2_traffic.json)
+    big_in = torch.cat([buf, buf, buf, buf])
+    big_out = torch.empty((1 << 24, 32), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    h2.hash_batch_device(big_in.data_ptr(), 1 << 24, big_out.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    print("ncu_probe headline ok")
+    sys.exit(0)
 h2.hash_batch_device(buf.data_ptr(), 1 << 22, out.data_ptr(), stream.cuda_stream)
 h5.hash_batch_device(buf.data_ptr(), 1 << 20, out.data_ptr(), stream.cuda_stream)
 level(2, 1 << 21)
