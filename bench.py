@@ -405,86 +405,121 @@ def run_ours(args, rank, world, local_rank):
                 assert rc in (0, 2), rc
             return timed(run), root.raw.hex(), idp.value, rdp.value
 
+        # Every leg below runs on its own: one that fails (a box short of pinned host memory, say) is
+        # recorded under roofline.configs.errors and the line is still printed with the others.
+        S = {}
+
+        def leg(fn):
+            try:
+                fn()
+            except Exception as e:                               # noqa: BLE001
+                extras.setdefault("errors", {})[fn.__name__] = repr(e)[:200]
+                torch.cuda.synchronize(dev)
+            return fn
+
         # O(1) callers (commitments, the coordinator-key hash, verify_outcome): ONE hash2 — device time of the
         # launch, the whole call from host buffers, and a second inf_init (tables cached per process, so this is
         # uploads + the two 32-link zero chains on the device)
-        one_in = device_random_fr(2, dev, seed=1)
-        one_out = torch.empty((1, 32), dtype=torch.uint8, device=dev)
-        dev_ms = timed(lambda: h2.hash_batch_device(one_in.data_ptr(), 1, one_out.data_ptr(), stream.cuda_stream), reps=5)
-        host_in = one_in.cpu().numpy()
-        call_ms = wall(lambda: h2.hash_batch(host_in, 1), reps=5)
-        t0 = time.perf_counter()
-        ctx2 = ib.Context(dev.index or 0)
-        init_ms = (time.perf_counter() - t0) * 1e3
-        ctx2.close()
-        e2e_more["single_hash2"] = {"device_us": dev_ms * 1e3, "call_us": call_ms * 1e3, "inf_init_ms": init_ms,
-                                    "api": "inf_poseidon_hash_batch(n=1): warp-cooperative kernel"}
+        @leg
+        def single_hash2():
+            one_in = device_random_fr(2, dev, seed=1)
+            one_out = torch.empty((1, 32), dtype=torch.uint8, device=dev)
+            dev_ms = timed(lambda: h2.hash_batch_device(one_in.data_ptr(), 1, one_out.data_ptr(), stream.cuda_stream), reps=5)
+            host_in = one_in.cpu().numpy()
+            call_ms = wall(lambda: h2.hash_batch(host_in, 1), reps=5)
+            t0 = time.perf_counter()
+            ctx2 = ib.Context(dev.index or 0)
+            init_ms = (time.perf_counter() - t0) * 1e3
+            ctx2.close()
+            e2e_more["single_hash2"] = {"device_us": dev_ms * 1e3, "call_us": call_ms * 1e3, "inf_init_ms": init_ms,
+                                        "api": "inf_poseidon_hash_batch(n=1): warp-cooperative kernel"}
+
         # small trees: the regime the reference's dev runtime lives in (65 536 participants)
-        lv = device_random_fr(1 << 16, dev, seed=16)
-        ms, _, _, _ = merge_dev_ms(2, 32, lv, True, False)
-        extras["state_tree_2^16"] = {"ms": ms, "hashes": (1 << 16) + 16}
+        @leg
+        def state_tree_2_16():
+            lv16 = device_random_fr(1 << 16, dev, seed=16)
+            ms, _, _, _ = merge_dev_ms(2, 32, lv16, True, False)
+            extras["state_tree_2^16"] = {"ms": ms, "hashes": (1 << 16) + 16}
+
         # configs[3] on one GPU: message-tree merge of 2^26 interaction leaves, arity 5, depth 12
-        lv = device_random_fr(1 << 26, dev, seed=26)
-        ms, root_hex5, idp, rdp = merge_dev_ms(5, 12, lv, False, True)
-        nh, c = 0, 1 << 26
-        for _ in range(12):
-            c = -(-c // 5)
-            nh += c
-        extras["message_tree_2^26"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
-                                       "root_depth": rdp, "root": root_hex5}
+        @leg
+        def message_tree_2_26():
+            S["lv"] = lv = device_random_fr(1 << 26, dev, seed=26)
+            ms, root_hex5, idp, rdp = merge_dev_ms(5, 12, lv, False, True)
+            nh, c = 0, 1 << 26
+            for _ in range(12):
+                c = -(-c // 5)
+                nh += c
+            extras["message_tree_2^26"] = {"ms": ms, "hashes": nh, "hashes_per_s": nh / (ms * 1e-3), "depth_field": idp,
+                                           "root_depth": rdp, "root": root_hex5}
+        if "lv" not in S:                                        # the later legs only need random elements
+            S["lv"] = device_random_fr(1 << 26, dev, seed=26)
+        lv = S["lv"]
+
         # end to end for the tree: 2^24 leaves in host memory -> root (inf_tree_merge uploads in chunks that
         # overlap with level-0 hashing), pinned and pageable
-        h_leaves = torch.empty((1 << 24, 32), dtype=torch.uint8).pin_memory()
-        h_leaves.copy_(lv[: 1 << 24])
-        root = C.create_string_buffer(32)
-        idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
+        @leg
+        def tree_merge_e2e():
+            h_leaves = torch.empty((1 << 24, 32), dtype=torch.uint8).pin_memory()
+            h_leaves.copy_(lv[: 1 << 24])
+            root = C.create_string_buffer(32)
+            idp, rdp, has = C.c_uint32(), C.c_uint32(), C.c_int()
 
-        def tree_from(arr):
-            def run():
-                rc = ctx.lib.inf_tree_merge(ctx.handle, 2, 24, 0, 1, arr.ctypes.data, 1 << 24, root, C.byref(idp),
-                                            C.byref(rdp), C.byref(has))
-                assert rc in (0, 2), rc
-            return run
-        hl = h_leaves.numpy()
-        pinned_ms = wall(tree_from(hl))
-        pg = np.empty((1 << 24, 32), dtype=np.uint8)
-        pg[:] = hl
-        pageable_ms = wall(tree_from(pg))
-        e2e_more["tree_merge_2^24"] = {"ms_pinned": pinned_ms, "ms_pageable": pageable_ms, "h2d_bytes": (1 << 24) * 32,
-                                       "d2h_bytes": 32, "api": "inf_tree_merge (host leaves -> root)", "root": root.raw.hex()}
-        del h_leaves, hl, pg
+            def tree_from(arr):
+                def run():
+                    rc = ctx.lib.inf_tree_merge(ctx.handle, 2, 24, 0, 1, arr.ctypes.data, 1 << 24, root, C.byref(idp),
+                                                C.byref(rdp), C.byref(has))
+                    assert rc in (0, 2), rc
+                return run
+            hl = h_leaves.numpy()
+            pinned_ms = wall(tree_from(hl))
+            pg = np.empty((1 << 24, 32), dtype=np.uint8)
+            pg[:] = hl
+            pageable_ms = wall(tree_from(pg))
+            e2e_more["tree_merge_2^24"] = {"ms_pinned": pinned_ms, "ms_pageable": pageable_ms, "h2d_bytes": (1 << 24) * 32,
+                                           "d2h_bytes": 32, "api": "inf_tree_merge (host leaves -> root)", "root": root.raw.hex()}
+
         # what a caller with ordinary (pageable) buffers sees: hash2 over 2^22 pairs, numpy arrays in and out
-        npg = 1 << 22
-        pg_in = np.empty((2 * npg, 32), dtype=np.uint8)
-        pg_in[:] = lv[: 2 * npg].cpu().numpy()
-        pg_out = np.empty((npg, 32), dtype=np.uint8)
-        h2.hash_batch(pg_in, npg, out=pg_out)
-        ms = wall(lambda: h2.hash_batch(pg_in, npg, out=pg_out))
-        e2e_more["hash2_2^22_pageable"] = {"ms": ms, "hashes_per_s": npg / (ms * 1e-3),
-                                           "api": "inf_poseidon_hash_batch (pageable host buffers)"}
-        del pg_in, pg_out
-        # hash5 batch (t = 6), 2^22 tuples
-        n5 = 1 << 22
-        d5 = lv[: 5 * n5]
-        o5 = torch.empty((n5, 32), dtype=torch.uint8, device=dev)
-        h5 = ib.Poseidon.new_circom(5, ctx)
-        ms = timed(lambda: h5.hash_batch_device(d5.data_ptr(), n5, o5.data_ptr(), stream.cuda_stream))
-        extras["hash5_2^22"] = {"ms": ms, "hashes_per_s": n5 / (ms * 1e-3)}
-        # next row: fused interaction-leaf hashing, 2^20 messages (2 x hash5 + hash4 each)
-        nm = 1 << 20
-        pk, dat = lv[: 2 * nm], lv[2 * nm: 12 * nm]
-        ol = torch.empty((nm, 32), dtype=torch.uint8, device=dev)
+        @leg
+        def hash2_pageable():
+            npg = 1 << 22
+            pg_in = np.empty((2 * npg, 32), dtype=np.uint8)
+            pg_in[:] = lv[: 2 * npg].cpu().numpy()
+            pg_out = np.empty((npg, 32), dtype=np.uint8)
+            h2.hash_batch(pg_in, npg, out=pg_out)
+            ms = wall(lambda: h2.hash_batch(pg_in, npg, out=pg_out))
+            e2e_more["hash2_2^22_pageable"] = {"ms": ms, "hashes_per_s": npg / (ms * 1e-3),
+                                               "api": "inf_poseidon_hash_batch (pageable host buffers)"}
 
-        def leaf_run():
-            rc = ctx.lib.inf_interaction_leaves_dev(ctx.handle, pk.data_ptr(), dat.data_ptr(), nm, ol.data_ptr(),
-                                                    stream.cuda_stream)
-            assert rc == 0
-        leaf_ms = timed(leaf_run)
-        extras["interaction_leaves_2^20"] = {"ms": leaf_ms, "messages_per_s": nm / (leaf_ms * 1e-3)}
-        ms5, _, _, _ = merge_dev_ms(5, 9, ol, False, True)
+        # hash5 batch (t = 6), 2^22 tuples
+        @leg
+        def hash5_batch():
+            n5 = 1 << 22
+            d5 = lv[: 5 * n5]
+            o5 = torch.empty((n5, 32), dtype=torch.uint8, device=dev)
+            h5 = ib.Poseidon.new_circom(5, ctx)
+            ms = timed(lambda: h5.hash_batch_device(d5.data_ptr(), n5, o5.data_ptr(), stream.cuda_stream))
+            extras["hash5_2^22"] = {"ms": ms, "hashes_per_s": n5 / (ms * 1e-3)}
+
+        # next row: fused interaction-leaf hashing, 2^20 messages (2 x hash5 + hash4 each)
+        @leg
+        def interaction_leaves():
+            nm = 1 << 20
+            pk, dat = lv[: 2 * nm], lv[2 * nm: 12 * nm]
+            ol = torch.empty((nm, 32), dtype=torch.uint8, device=dev)
+
+            def leaf_run():
+                rc = ctx.lib.inf_interaction_leaves_dev(ctx.handle, pk.data_ptr(), dat.data_ptr(), nm, ol.data_ptr(),
+                                                        stream.cuda_stream)
+                assert rc == 0
+            leaf_ms = timed(leaf_run)
+            extras["interaction_leaves_2^20"] = {"ms": leaf_ms, "messages_per_s": nm / (leaf_ms * 1e-3)}
+            ms5, _, _, _ = merge_dev_ms(5, 9, ol, False, True)
+            S["leaf_plus_tree_ms"] = leaf_ms + ms5
+
         # replay: raw messages in host memory -> leaves -> merged tree, nothing but the root coming back
         # (inf_replay_interactions); compared with leaf time + tree time on device-resident data
-        for log_m, kinds in ((20, ("pinned", "pageable")), (24, ("pinned",))):
+        def replay(log_m, kinds):
             m = 1 << log_m
             h_pk = torch.empty((m, 64), dtype=torch.uint8).pin_memory()
             h_dat = torch.empty((m, 320), dtype=torch.uint8).pin_memory()
@@ -509,11 +544,19 @@ def run_ours(args, rank, world, local_rank):
                 row["ms_" + kind] = wall(run, reps=2)
                 row["root"] = res["root"]
             row["messages_per_s"] = m / (row["ms_pinned"] * 1e-3)
-            if log_m == 20:
-                row["leaf_ms_plus_tree_ms_device"] = leaf_ms + ms5
+            if log_m == 20 and "leaf_plus_tree_ms" in S:
+                row["leaf_ms_plus_tree_ms_device"] = S["leaf_plus_tree_ms"]
             e2e_more["replay_interactions_2^%d" % log_m] = row
-            del h_pk, h_dat
-        del lv, d5, o5, pk, dat, ol
+
+        @leg
+        def replay_2_20():
+            replay(20, ("pinned", "pageable"))
+
+        @leg
+        def replay_2_24():
+            replay(24, ("pinned",))
+        del lv
+        S.clear()
         torch.cuda.empty_cache()
 
     # ---- the in-library multi-GPU path (inf_multi_*: ONE process drives all N GPUs; what a Rust host calls),
