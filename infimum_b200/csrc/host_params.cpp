@@ -255,6 +255,69 @@ std::vector<uint32_t> build_opt(void) {
         put_mont(tbl, L::COOP_C + j, c);
     }
     for (int i = 1; i < T; i++) put_mont(tbl, L::LAST_D + i - 1, D[i]);
+    if constexpr (L::FB) {
+        // functional basis for width 3 (Layout::FB; derive_fb in tests/opt_model.py)
+        static_assert(!L::FB || T == 3, "functional basis is derived for width 3");
+        struct Fn { F f[2]; F c; };
+        // the two functionals (vector, constant) read when the partial section resumes at round j
+        auto functionals = [&](int j, Fn& f1, Fn& f2) {
+            if (j + 1 < rp) {
+                f1 = Fn{{vs[j][0], vs[j][1]}, ks[j]};
+                f2 = Fn{{vs[j + 1][0], vs[j + 1][1]}, ks[j + 1]};
+            } else if (j < rp) {                      // odd count: the single round's row, and s[2] itself
+                f1 = Fn{{vs[j][0], vs[j][1]}, ks[j]};
+                f2 = Fn{{zero(), one()}, zero()};
+            } else {                                  // even count: the state itself, tail constants folded in
+                f1 = Fn{{one(), zero()}, D[1]};
+                f2 = Fn{{zero(), one()}, D[2]};
+            }
+        };
+        Fn f1, f2;
+        functionals(0, f1, f2);
+        for (int x = 0; x < T; x++) {
+            put_mont(tbl, L::FB_PRE_M + x, PRE[x]);
+            put_mont(tbl, L::FB_PRE_M + T + x, add(mul(f1.f[0], PRE[T + x]), mul(f1.f[1], PRE[2 * T + x])));
+            put_mont(tbl, L::FB_PRE_M + 2 * T + x, add(mul(f2.f[0], PRE[T + x]), mul(f2.f[1], PRE[2 * T + x])));
+        }
+        put_v(tbl, L::FB_PRE_V + 0, k[0]);
+        put_v(tbl, L::FB_PRE_V + 1, f1.c);
+        put_v(tbl, L::FB_PRE_V + 2, f2.c);
+        for (int jp = 0; jp < rp / 2; jp++) {
+            const int a = 2 * jp, b = 2 * jp + 1, base = L::FB_PART + jp * L::FB_STRIDE;
+            const F det = sub(mul(vs[a][0], vs[b][1]), mul(vs[a][1], vs[b][0]));
+            if (det.is_zero()) throw std::runtime_error("dependent rows in the functional basis");
+            const F di = inv(det);
+            // [v_A; v_B]^-1
+            const F vi[2][2] = {{mul(vs[b][1], di), sub(zero(), mul(vs[a][1], di))},
+                                {sub(zero(), mul(vs[b][0], di)), mul(vs[a][0], di)}};
+            put_mont(tbl, base + L::FB_C, add(mul(vs[b][0], ws[a][0]), mul(vs[b][1], ws[a][1])));
+            functionals(a + 2, f1, f2);
+            const Fn* fn[2] = {&f1, &f2};
+            const int g_at[2] = {L::FB_GA, L::FB_GB}, k_at[2] = {L::FB_KA, L::FB_KB};
+            for (int r = 0; r < 2; r++) {
+                const F* f = fn[r]->f;
+                const F g0 = add(mul(f[0], vi[0][0]), mul(f[1], vi[1][0]));
+                const F g1 = add(mul(f[0], vi[0][1]), mul(f[1], vi[1][1]));
+                put_mont(tbl, base + g_at[r] + 0, g0);
+                put_mont(tbl, base + g_at[r] + 1, g1);
+                put_mont(tbl, base + g_at[r] + 2, add(mul(f[0], ws[a][0]), mul(f[1], ws[a][1])));
+                put_mont(tbl, base + g_at[r] + 3, add(mul(f[0], ws[b][0]), mul(f[1], ws[b][1])));
+                put_v(tbl, base + k_at[r], sub(fn[r]->c, add(mul(g0, ks[a]), mul(g1, ks[b]))));
+            }
+        }
+        if (rp % 2) {
+            const int j = rp - 1;
+            if (vs[j][0].is_zero()) throw std::runtime_error("zero pivot in the last functional-basis round");
+            const F i0 = inv(vs[j][0]);
+            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 0, i0);
+            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 1, sub(zero(), mul(vs[j][1], i0)));
+            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 2, ws[j][0]);
+            put_v(tbl, L::FB_LAST + L::FB_L_K1, sub(D[1], mul(ks[j], i0)));
+            put_mont(tbl, L::FB_LAST + L::FB_L_W2, ws[j][1]);
+            put_v(tbl, L::FB_LAST + L::FB_L_D2, D[2]);
+        }
+    }
+    put_mont(tbl, L::X0, pow5(C(0, 0)));
     for (int r = 0; r < 3; r++)
         for (int i = 0; i < T; i++) put_v(tbl, L::TAIL_V + r * T + i, C(half + rp + r + 1, i));
     for (int j = 0; j < T; j++) {

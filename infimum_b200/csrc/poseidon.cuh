@@ -70,6 +70,13 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 // plain sparse form, and nothing but an addition between one S-box and the next.
 // The scale comes off in the first round of the second half, whose matrix has
 // column 0 multiplied by lambda_RP^5 (TAIL0_M).
+// Widths whose per-thread kernels run the partial rounds in the functional basis (Layout::FB).
+#ifdef INF_NO_FB
+INF_HD constexpr bool fb_rounds(int) { return false; }
+#else
+INF_HD constexpr bool fb_rounds(int t) { return t == 3; }
+#endif
+
 template <int T>
 struct Layout {
     static constexpr int RP = partial_rounds(T);
@@ -98,7 +105,28 @@ struct Layout {
     // c_j = v'_j . w'_{j-1} for every partial round j (c_0 = 0): lets the warp-cooperative
     // kernel (coop.cuh) form v'_j . s[1..] from the state of one round earlier
     static constexpr int COOP_C = OUT_ROW_MONT + T;      // [RP]
-    static constexpr int COUNT = COOP_C + RP;
+    // Functional basis (width 3 only; derive_fb in tests/opt_model.py).  The two passive state
+    // elements are carried as the two functionals the NEXT pair of rounds reads,
+    //     a = v'_A . s[1..] + k'_A ,   b = v'_B . s[1..] + k'_B ,
+    // which a two-dimensional s[1..] is determined by, so a pair of rounds becomes
+    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a
+    //     a' = ga . (a, b, z_a, z_b) + ka ;  b' = gb . (a, b, z_a, z_b) + kb
+    // 9 products and 3 reductions instead of 9 and 4 (-4.6 % multiply-pipe instructions per
+    // pair).  For wider states the coordinate change costs more than the reduction it saves.
+    // The per-thread kernels use these records; the warp-cooperative schedule keeps the ones above.
+    static constexpr bool FB = fb_rounds(T);
+    static constexpr int FB_PRE_M = COOP_C + RP;         // [T][T] rows 1, 2 of PRE_M mapped to (a_0, b_0)
+    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_0, k'_1)
+    static constexpr int FB_PART = FB_PRE_V + T;         // RP/2 records: c, ga[4], ka, gb[4], kb
+    static constexpr int FB_STRIDE = 11;
+    static constexpr int FB_C = 0, FB_GA = 1, FB_KA = 5, FB_GB = 6, FB_KB = 10;
+    // odd RP, the last round: s_1 = g1 . (a, b, z) + k1 ; s_2 = b + w2 z + d2 (constants D folded in)
+    static constexpr int FB_LAST = FB_PART + (RP / 2) * FB_STRIDE;
+    static constexpr int FB_L_G1 = 0, FB_L_K1 = 3, FB_L_W2 = 4, FB_L_D2 = 5, FB_L_COUNT = 6;
+    // (C_0[0])^5: what the first S-box makes of state[0] when the domain tag is zero (every circom
+    // hasher, every tree node) -- a constant, so round 0 takes it from here instead of computing it
+    static constexpr int X0 = FB ? FB_LAST + (RP % 2) * FB_L_COUNT : COOP_C + RP;
+    static constexpr int COUNT = X0 + 1;
     static constexpr int WORDS = COUNT * 8;
     // offsets inside a pair record
     static constexpr int P_VA = 0, P_KA = T - 1, P_VB = T, P_CB = 2 * T - 1, P_KB = 2 * T, P_W = 2 * T + 1;
@@ -133,8 +161,9 @@ INF_HD void sbox(uint32_t (&y)[8], const uint32_t (&x)[8]) {
 // form, every element < 2p + eps.  On return `out` holds state[0] after the
 // last round: canonical integer in [0, p) if !MONT_OUT, Montgomery form
 // (< 2p + eps) if MONT_OUT.
+// `tag0`: state[0] is the table's S0 (domain tag zero), so its first S-box output is the table's X0.
 template <int T, bool MONT_OUT>
-INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint32_t* tbl) {
+INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint32_t* tbl, const bool tag0 = false) {
     using L = Layout<T>;
     static_assert(T >= 2 && T <= 8, "optimised path covers widths 2..8");
     uint32_t x[T][8];
@@ -146,15 +175,64 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     // ---- first half: rounds 0..3 (round 3 uses the merged matrix) ----------
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::PRE_M) * 8;
-        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::PRE_V) * 8;
+        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::FB ? L::FB_PRE_M : L::PRE_M) * 8;
+        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::FB ? L::FB_PRE_V : L::PRE_V) * 8;
         INF_LOCKSTEP_SYNC();
+        if (r == 0 && tag0) {
 #pragma unroll
-        for (int i = 0; i < T; i++) sbox(x[i], s[i]);
+            for (int k = 0; k < 8; k++) x[0][k] = tbl[L::X0 * 8 + k];
+        } else {
+            sbox(x[0], s[0]);
+        }
+#pragma unroll
+        for (int i = 1; i < T; i++) sbox(x[i], s[i]);
 #pragma unroll
         for (int i = 0; i < T; i++) dot<T, 8, RS>(s[i], &x[0][0], m + i * T * 8, v + i * 8);
     }
 
+    if constexpr (L::FB) {
+        // ---- partial rounds, functional basis (Layout::FB): s = (u, a, b) ------------------
+        // q = (a, b, z_a, z_b), contiguous for the four-term rows.  Ranges: a, b < 2p + eps (range
+        // step of their rows), z < 1.7 p, so n = z_a + a and u' = z_b + (b + c z_a) are below 3.7 p
+        // before their range steps, and b + c z_a < 2p + 1.33 p.
+        static_assert(!L::FB || T == 3, "functional basis is derived for width 3");
+        uint32_t q[4][8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[0][k] = s[1][k], q[1][k] = s[2][k];
+#pragma unroll 1
+        for (int j = 0; j < L::RP / 2; j++) {
+            const uint32_t* pt = tbl + (L::FB_PART + j * L::FB_STRIDE) * 8;
+            uint32_t n[8], m[8], na[8];
+            INF_LOCKSTEP_SYNC();
+            sbox(q[2], s[0]);                                                   // z_a = u^5
+            add8(n, q[2], q[0]);
+            csub2p(n);
+            mont_mul(m, q[2], pt + L::FB_C * 8);                                // b + c z_a
+            add8(m, m, q[1]);
+            csub2p(m);
+            sbox(q[3], n);                                                      // z_b = n^5
+            add8(s[0], q[3], m);
+            csub2p(s[0]);
+            dot<4, 8, true>(na, &q[0][0], pt + L::FB_GA * 8, pt + L::FB_KA * 8);
+            dot<4, 8, true>(q[1], &q[0][0], pt + L::FB_GB * 8, pt + L::FB_KB * 8);   // reads q[1] before writing it: see dot
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[0][k] = na[k];
+        }
+        if constexpr (L::RP % 2 == 1) {
+            const uint32_t* pt = tbl + L::FB_LAST * 8;
+            uint32_t w[8];
+            sbox(q[2], s[0]);
+            add8(s[0], q[2], q[0]);
+            csub2p(s[0]);
+            dot<3, 8, true>(s[1], &q[0][0], pt + L::FB_L_G1 * 8, pt + L::FB_L_K1 * 8);
+            mont_mul_add(w, q[2], pt + L::FB_L_W2 * 8, pt + L::FB_L_D2 * 8);
+            add8(s[2], q[1], w);
+            csub2p(s[2]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[1][k] = q[0][k], s[2][k] = q[1][k];
+        }
+    } else {
     // ---- partial rounds -----------------------------------------------------
     // q[0..T-2] = s[1..T-1], q[T-1] = z_a, q[T] = z_b: contiguous, so that the lazy
     // dots stride over (s[1..], z_a) and (z_a, z_b).  s[0] holds u.
@@ -215,6 +293,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     for (int i = 1; i < T; i++) {
         add8(s[i], s[i], tbl + (L::LAST_D + i - 1) * 8);
         csub2p(s[i]);
+    }
     }
 
     // ---- second half: 3 full rounds, then the output row --------------------
@@ -301,7 +380,7 @@ INF_HD void hash_words(uint32_t (&out_words)[8], const uint32_t (&in_words)[T - 
         absorb<T>(s[i], raw, i, tbl);
     }
     uint32_t h[8];
-    poseidon_rounds<T, false>(h, s, tbl);
+    poseidon_rounds<T, false>(h, s, tbl, tag_words == nullptr);
     limbs_to_words<LE>(out_words, h);
 }
 

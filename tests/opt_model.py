@@ -212,3 +212,98 @@ def hash_opt_scaled(inputs, tag=0, tables=None, paired_rounds=True):
         if r + 1 < 8 + rp:
             s = [(a + b) % P for a, b in zip(s, C[r + 1])]
     return s[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# Functional basis for width 3 (round 2, Layout<3>::FB in poseidon.cuh)
+# ---------------------------------------------------------------------------------------------
+def derive_fb(t=3, tables=None):
+    """Partial rounds of width 3 with the two passive state elements carried as the two
+    linear functionals the NEXT pair of rounds reads, instead of as themselves.
+
+    In the unit-leading form (derive) a pair of rounds A, B is
+        z_a = u^5 ; n = z_a + v_A.rest + k_A ; z_b = n^5 ; u' = z_b + v_B.rest + c z_a + k_B
+        rest' = rest + w_A z_a + w_B z_b                         (c = v_B.w_A)
+    i.e. 9 products and 4 reductions.  `rest` is two-dimensional, so it is determined by
+        a = v_A.rest + k_A ,  b = v_B.rest + k_B
+    (the 2x2 matrix [v_A; v_B] is invertible for these parameters), and the pair becomes
+        z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a
+        a' = ga.(a, b, z_a, z_b) + ka ,  b' = gb.(a, b, z_a, z_b) + kb
+    with a', b' the functionals of the next pair: 9 products, 3 reductions.  The first (a, b)
+    come out of the merged round-3 matrix (rows 1, 2 of PRE replaced by v_0.PRE[1:], v_1.PRE[1:]);
+    an odd round count ends with one single round that reads a = v.rest + k and b = rest[1] and
+    returns the plain state elements (constants D folded in) to the second half."""
+    assert t == 3
+    T = tables or derive(t)
+    rp, sc, D, PRE = T["rp"], T["scaled"], T["D"], T["PRE"]
+    n_pairs = rp // 2
+    inv = lambda x: pow(x, P - 2, P)
+
+    def functionals(j):
+        """The two functionals (vector, constant) read when the section resumes at round j."""
+        if j + 1 < rp:
+            return (sc[j][0], sc[j][2]), (sc[j + 1][0], sc[j + 1][2])
+        if j < rp:                                   # odd count: the single round's row, and rest[1] itself
+            return (sc[j][0], sc[j][2]), ([0, 1], 0)
+        return ([1, 0], D[1]), ([0, 1], D[2])        # even count: the state itself, constants of the tail folded in
+
+    (f1, c1), (f2, c2) = functionals(0)
+    pre = [list(PRE[0]),
+           [(f1[0] * PRE[1][x] + f1[1] * PRE[2][x]) % P for x in range(3)],
+           [(f2[0] * PRE[1][x] + f2[1] * PRE[2][x]) % P for x in range(3)]]
+    pre_v = [T["k"][0], c1, c2]
+    pairs = []
+    for p in range(n_pairs):
+        A, B = 2 * p, 2 * p + 1
+        (vA, wA, kA), (vB, wB, kB) = sc[A], sc[B]
+        det = (vA[0] * vB[1] - vA[1] * vB[0]) % P
+        assert det != 0
+        di = inv(det)
+        Vi = [[vB[1] * di % P, -vA[1] * di % P], [-vB[0] * di % P, vA[0] * di % P]]   # [v_A; v_B]^-1
+        c = (vB[0] * wA[0] + vB[1] * wA[1]) % P
+        rows = []
+        for f, const in functionals(A + 2):
+            g = [(f[0] * Vi[0][x] + f[1] * Vi[1][x]) % P for x in range(2)]         # f . V^-1
+            ga = [g[0], g[1], (f[0] * wA[0] + f[1] * wA[1]) % P, (f[0] * wB[0] + f[1] * wB[1]) % P]
+            rows.append((ga, (const - g[0] * kA - g[1] * kB) % P))
+        pairs.append((c, rows[0], rows[1]))
+    last = None
+    if rp % 2:
+        v, w, k = sc[rp - 1]
+        assert v[0] != 0
+        i0 = inv(v[0])
+        # rest_0 = (a - k - v_1 b) / v_0 ; s_1' = rest_0 + w_0 z + D_1 ; s_2' = b + w_1 z + D_2
+        last = dict(g1=[i0, -v[1] * i0 % P, w[0]], k1=(D[1] - k * i0) % P, w2=w[1], d2=D[2])
+    return dict(pre=pre, pre_v=pre_v, pairs=pairs, last=last)
+
+
+def hash_opt_fb(inputs, tag=0, tables=None, fb=None):
+    """Width 3 through the functional-basis partial rounds (derive_fb)."""
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    F = fb or derive_fb(t, T)
+    rp, M, C = T["rp"], T["M"], T["C"]
+    sb = lambda x: pow(x, 5, P)
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    u, a, b = [(x + y) % P for x, y in zip(_matvec(F["pre"], [sb(x) for x in s]), F["pre_v"])]
+    for c, (ga, ka), (gb, kb) in F["pairs"]:
+        za = sb(u)
+        n = (za + a) % P
+        zb = sb(n)
+        u = (zb + b + c * za) % P
+        q = (a, b, za, zb)
+        a, b = (sum(x * y for x, y in zip(ga, q)) + ka) % P, (sum(x * y for x, y in zip(gb, q)) + kb) % P
+    if F["last"]:
+        L = F["last"]
+        z = sb(u)
+        u = (z + a) % P
+        a, b = (L["g1"][0] * a + L["g1"][1] * b + L["g1"][2] * z + L["k1"]) % P, (b + L["w2"] * z + L["d2"]) % P
+    s = _matvec(T["TAIL0"], [sb(u), sb(a), sb(b)])
+    s = [(x + y) % P for x, y in zip(s, C[4 + rp + 1])]
+    for r in range(4 + rp + 1, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(x + y) % P for x, y in zip(s, C[r + 1])]
+    return s[0]

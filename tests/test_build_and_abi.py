@@ -86,8 +86,10 @@ def test_executed_multiply_count_per_hash2():
     obj = os.path.join(root, "infimum_b200", "_build", "poseidon_t3.o")
     for fn in ("hash_batch_kernelILb0", "17tree_level_kernel"):
         c = sass_count.count(obj, fn, [4, 28, 3])
-        assert 50000 < c["wide"] <= 57000 and c["hi"] <= 3200 and c["imad"] <= 3200, c
-        assert sum(c.values()) <= 90000, c
+        # 28 functional-basis pairs (9 products, 3 reductions each) + one last round; the static count
+        # still includes round 0's S-box of the constant state[0], skipped at run time under tag 0
+        assert 50000 < c["wide"] <= 52000 and c["hi"] <= 2900 and c["imad"] <= 2900, c
+        assert sum(c.values()) <= 84000, c
 
 
 def test_product_does_not_import_oracle():

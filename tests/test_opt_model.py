@@ -39,3 +39,15 @@ def test_unit_leading_coefficient_schedule_equals_dense(t):
             exp = O.poseidon_permute_hash(ins, tag)
             assert opt_model.hash_opt_scaled(ins, tag, tables, True) == exp
             assert opt_model.hash_opt_scaled(ins, tag, tables, False) == exp
+
+
+def test_functional_basis_schedule_equals_dense():
+    """Width 3 with the passive state carried as the next pair's two functionals (Layout<3>::FB)."""
+    T = opt_model.derive(3)
+    F = opt_model.derive_fb(3, T)
+    assert len(F["pairs"]) == 28 and F["last"] is not None
+    rng = random.Random(33)
+    for i in range(12):
+        ins = [rng.randrange(O.P) for _ in range(2)]
+        tag = 0 if i % 3 else rng.randrange(O.P)
+        assert opt_model.hash_opt_fb(ins, tag, T, F) == O.poseidon_permute_hash(ins, tag)
