@@ -419,6 +419,34 @@ INF_HD void csub2p(uint32_t (&x)[8]) {
 #endif
 }
 
+// The same step for 4p: afterwards x < max(4p + 2^224, bound_before - 4p).  Any 256-bit
+// integer (< 5.29 p) is below 4p + 2^224 after it, and below 2p + 2^224 after csub2p.
+INF_HD void csub4p(uint32_t (&x)[8]) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.gt.u32      q, %7, 0xc19139cb;\n\t"
+        "@q sub.cc.u32    %0, %0, 0xc0000004;\n\t"
+        "@q subc.cc.u32   %1, %1, 0x0f87d64f;\n\t"
+        "@q subc.cc.u32   %2, %2, 0xe6e5c245;\n\t"
+        "@q subc.cc.u32   %3, %3, 0xa0cfa121;\n\t"
+        "@q subc.cc.u32   %4, %4, 0x06056174;\n\t"
+        "@q subc.cc.u32   %5, %5, 0xe14116da;\n\t"
+        "@q subc.cc.u32   %6, %6, 0x84c680a6;\n\t"
+        "@q subc.u32      %7, %7, 0xc19139cb;\n\t"
+        "}"
+        : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]),
+          "+r"(x[7]));
+#else
+    if (x[7] > 0xc19139cbu) {
+        uint32_t d[8];
+        sub8(d, x, 0xc0000004u, 0x0f87d64fu, 0xe6e5c245u, 0xa0cfa121u, 0x06056174u, 0xe14116dau, 0x84c680a6u,
+             0xc19139cbu);
+        for (int i = 0; i < 8; i++) x[i] = d[i];
+    }
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // The lazy Montgomery accumulator.
 // ---------------------------------------------------------------------------

@@ -317,7 +317,19 @@ std::vector<uint32_t> build_opt(void) {
             put_v(tbl, L::FB_LAST + L::FB_L_D2, D[2]);
         }
     }
-    put_mont(tbl, L::X0, pow5(C(0, 0)));
+    {
+        // round 0 on unconverted inputs (Layout::R0_M): M R^6, (C_0[0])^5 / R^4, C_0 canonical.
+        // to_mont multiplies by R, from_mont divides by it.
+        for (int i = 0; i < T * T; i++) {
+            F x = M[i];
+            for (int e = 0; e < 6; e++) x = to_mont(x);
+            to_limbs32(x, &tbl[(L::R0_M + i) * 8]);
+        }
+        F x0 = pow5(C(0, 0));
+        for (int e = 0; e < 4; e++) x0 = from_mont(x0);
+        to_limbs32(x0, &tbl[L::X0 * 8]);
+        for (int i = 0; i < T; i++) put_canon(tbl, L::IN_C + i, C(0, i));
+    }
     for (int r = 0; r < 3; r++)
         for (int i = 0; i < T; i++) put_v(tbl, L::TAIL_V + r * T + i, C(half + rp + r + 1, i));
     for (int j = 0; j < T; j++) {

@@ -126,7 +126,13 @@ struct Layout {
     // (C_0[0])^5: what the first S-box makes of state[0] when the domain tag is zero (every circom
     // hasher, every tree node) -- a constant, so round 0 takes it from here instead of computing it
     static constexpr int X0 = FB ? FB_LAST + (RP % 2) * FB_L_COUNT : COOP_C + RP;
-    static constexpr int COUNT = X0 + 1;
+    // Round 0 of the per-thread kernels runs on the inputs as they arrive, x + C_0 as a plain integer
+    // (absorb_raw) instead of (x + C_0) R: the S-box then yields s^5 / R^4, and the round's matrix
+    // carries the missing R^5 (R0_M = M R^6 against FULL_M = M R), so no input pays a conversion
+    // product.  X0 is stored in the same scale, (C_0[0])^5 / R^4.  IN_C = C_0 as canonical integers.
+    static constexpr int R0_M = X0 + 1;                  // [T][T]
+    static constexpr int IN_C = R0_M + T * T;            // [T]
+    static constexpr int COUNT = IN_C + T;
     static constexpr int WORDS = COUNT * 8;
     // offsets inside a pair record
     static constexpr int P_VA = 0, P_KA = T - 1, P_VB = T, P_CB = 2 * T - 1, P_KB = 2 * T, P_W = 2 * T + 1;
@@ -163,7 +169,9 @@ INF_HD void sbox(uint32_t (&y)[8], const uint32_t (&x)[8]) {
 // (< 2p + eps) if MONT_OUT.
 // `tag0`: state[0] is the table's S0 (domain tag zero), so its first S-box output is the table's X0.
 template <int T, bool MONT_OUT>
-INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint32_t* tbl, const bool tag0 = false) {
+// `raw_in`: s came from absorb_raw (round 0 then uses R0_M, see Layout).
+INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint32_t* tbl, const bool tag0 = false,
+                            const bool raw_in = false) {
     using L = Layout<T>;
     static_assert(T >= 2 && T <= 8, "optimised path covers widths 2..8");
     uint32_t x[T][8];
@@ -175,7 +183,7 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     // ---- first half: rounds 0..3 (round 3 uses the merged matrix) ----------
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-        const uint32_t* m = tbl + (r < 3 ? L::FULL_M : L::FB ? L::FB_PRE_M : L::PRE_M) * 8;
+        const uint32_t* m = tbl + (r == 0 && raw_in ? L::R0_M : r < 3 ? L::FULL_M : L::FB ? L::FB_PRE_M : L::PRE_M) * 8;
         const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::FB ? L::FB_PRE_V : L::PRE_V) * 8;
         INF_LOCKSTEP_SYNC();
         if (r == 0 && tag0) {
@@ -335,6 +343,25 @@ INF_HD void absorb(uint32_t (&s)[8], const uint32_t (&raw)[8], int i, const uint
     // (0.189 * 5.29 + 1) p < 2p: already in range
 }
 
+// The same element left as a plain integer: x + C_0[i] mod p, below 2p + 2^224 (what the
+// squaring that follows needs is < 2^255 = 2.645 p).  No product: three conditional
+// subtractions and one addition.  Round 0 must then run against R0_M (Layout).
+template <int T>
+INF_HD void absorb_raw(uint32_t (&s)[8], const uint32_t (&raw)[8], int i, const uint32_t* tbl) {
+    using L = Layout<T>;
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = raw[k];
+    csub4p(x);                                              // any 256-bit integer -> < 4p + 2^224
+    csub2p(x);                                              // < 2p + 2^224
+    uint32_t c = add8(s, x, tbl + (L::IN_C + i) * 8);       // + C_0[i] (< p): < 3p + 2^224, no carry
+    (void)c;
+#if defined(INF_HOST_CHECKS) && !defined(__CUDA_ARCH__)
+    if (c) host_overflow_count++;
+#endif
+    csub2p(s);                                              // < 2p + 2^224
+}
+
 // 32-byte wire format (pallet/src/poll/poll.rs:9 `HashBytes`, big-endian; the
 // little-endian variant serves hash_bytes_le, poseidon.rs:233-250) <-> limbs.
 // w[] are the eight 32-bit words as loaded from memory.
@@ -368,19 +395,20 @@ INF_HD void hash_words(uint32_t (&out_words)[8], const uint32_t (&in_words)[T - 
 #pragma unroll
         for (int k = 0; k < 8; k++) w[k] = tag_words[k];
         words_to_limbs<LE>(raw, w);
-        absorb<T>(s[0], raw, 0, tbl);
+        absorb_raw<T>(s[0], raw, 0, tbl);
     } else {
+        // tag 0: round 0 reads X0 instead of s[0]; keep the register contents defined
 #pragma unroll
-        for (int k = 0; k < 8; k++) s[0][k] = tbl[L::S0 * 8 + k];
+        for (int k = 0; k < 8; k++) s[0][k] = 0;
     }
 #pragma unroll
     for (int i = 1; i < T; i++) {
         uint32_t raw[8];
         words_to_limbs<LE>(raw, in_words[i - 1]);
-        absorb<T>(s[i], raw, i, tbl);
+        absorb_raw<T>(s[i], raw, i, tbl);
     }
     uint32_t h[8];
-    poseidon_rounds<T, false>(h, s, tbl, tag_words == nullptr);
+    poseidon_rounds<T, false>(h, s, tbl, tag_words == nullptr, true);
     limbs_to_words<LE>(out_words, h);
 }
 

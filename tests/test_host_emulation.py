@@ -199,7 +199,13 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
         assert el(k) == vform(L["k1"]); k += 1
         assert el(k) == mont(L["w2"]); k += 1
         assert el(k) == vform(L["d2"]); k += 1
-    assert el(k) == mont(pow(T["C"][0][0], 5, P)); k += 1      # X0: first S-box of state[0] under tag 0
+    # round 0 on unconverted inputs: X0 = (C_0[0])^5 / R^4, R0_M = M R^6, IN_C = C_0
+    assert el(k) == pow(T["C"][0][0], 5, P) * pow(R, -4, P) % P; k += 1
+    for i in range(t):
+        for j in range(t):
+            assert el(k) == T["M"][i][j] * pow(R, 6, P) % P; k += 1
+    for i in range(t):
+        assert el(k) == T["C"][0][i]; k += 1
     assert k * 8 == words
 
 
