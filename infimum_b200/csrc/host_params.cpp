@@ -256,66 +256,71 @@ std::vector<uint32_t> build_opt(void) {
     }
     for (int i = 1; i < T; i++) put_mont(tbl, L::LAST_D + i - 1, D[i]);
     if constexpr (L::FB) {
-        // functional basis for width 3 (Layout::FB; derive_fb in tests/opt_model.py)
-        static_assert(!L::FB || T == 3, "functional basis is derived for width 3");
-        struct Fn { F f[2]; F c; };
-        // the two functionals (vector, constant) read when the partial section resumes at round j
-        auto functionals = [&](int j, Fn& f1, Fn& f2) {
-            if (j + 1 < rp) {
-                f1 = Fn{{vs[j][0], vs[j][1]}, ks[j]};
-                f2 = Fn{{vs[j + 1][0], vs[j + 1][1]}, ks[j + 1]};
-            } else if (j < rp) {                      // odd count: the single round's row, and s[2] itself
-                f1 = Fn{{vs[j][0], vs[j][1]}, ks[j]};
-                f2 = Fn{{zero(), one()}, zero()};
-            } else {                                  // even count: the state itself, tail constants folded in
-                f1 = Fn{{one(), zero()}, D[1]};
-                f2 = Fn{{zero(), one()}, D[2]};
-            }
-        };
-        Fn f1, f2;
-        functionals(0, f1, f2);
-        for (int x = 0; x < T; x++) {
-            put_mont(tbl, L::FB_PRE_M + x, PRE[x]);
-            put_mont(tbl, L::FB_PRE_M + T + x, add(mul(f1.f[0], PRE[T + x]), mul(f1.f[1], PRE[2 * T + x])));
-            put_mont(tbl, L::FB_PRE_M + 2 * T + x, add(mul(f2.f[0], PRE[T + x]), mul(f2.f[1], PRE[2 * T + x])));
-        }
-        put_v(tbl, L::FB_PRE_V + 0, k[0]);
-        put_v(tbl, L::FB_PRE_V + 1, f1.c);
-        put_v(tbl, L::FB_PRE_V + 2, f2.c);
-        for (int jp = 0; jp < rp / 2; jp++) {
-            const int a = 2 * jp, b = 2 * jp + 1, base = L::FB_PART + jp * L::FB_STRIDE;
-            const F det = sub(mul(vs[a][0], vs[b][1]), mul(vs[a][1], vs[b][0]));
+        // width 3: rows over Q = (a, u', z_a, z_b) (Layout::FB; derive_fb2 in tests/opt_model.py)
+        static_assert(!L::FB || T == 3, "derived for width 3");
+        if (rp % 2 != 1) throw std::runtime_error("functional basis expects an odd round count");
+        auto dot2 = [](const F* x, const std::vector<F>& y) { return add(mul(x[0], y[0]), mul(x[1], y[1])); };
+        struct M2 { F m[2][2]; };
+        auto inv2 = [](const std::vector<F>& r0, const std::vector<F>& r1) {
+            const F det = sub(mul(r0[0], r1[1]), mul(r0[1], r1[0]));
             if (det.is_zero()) throw std::runtime_error("dependent rows in the functional basis");
             const F di = inv(det);
-            // [v_A; v_B]^-1
-            const F vi[2][2] = {{mul(vs[b][1], di), sub(zero(), mul(vs[a][1], di))},
-                                {sub(zero(), mul(vs[b][0], di)), mul(vs[a][0], di)}};
-            put_mont(tbl, base + L::FB_C, add(mul(vs[b][0], ws[a][0]), mul(vs[b][1], ws[a][1])));
-            functionals(a + 2, f1, f2);
-            const Fn* fn[2] = {&f1, &f2};
-            const int g_at[2] = {L::FB_GA, L::FB_GB}, k_at[2] = {L::FB_KA, L::FB_KB};
+            return M2{{{mul(r1[1], di), neg(mul(r0[1], di))}, {neg(mul(r1[0], di)), mul(r0[0], di)}}};
+        };
+        for (int x = 0; x < T; x++) {
+            put_mont(tbl, L::FB_PRE_M + x, PRE[x]);
+            put_mont(tbl, L::FB_PRE_M + T + x, add(mul(vs[1][0], PRE[T + x]), mul(vs[1][1], PRE[2 * T + x])));
+            put_mont(tbl, L::FB_PRE_M + 2 * T + x, add(mul(vs[2][0], PRE[T + x]), mul(vs[2][1], PRE[2 * T + x])));
+        }
+        put_v(tbl, L::FB_PRE_V + 0, k[0]);
+        put_v(tbl, L::FB_PRE_V + 1, ks[1]);
+        put_v(tbl, L::FB_PRE_V + 2, ks[2]);
+        {   // v_0 = al v_1 + be v_2
+            const M2 vi = inv2(vs[1], vs[2]);
+            const F al = add(mul(vs[0][0], vi.m[0][0]), mul(vs[0][1], vi.m[1][0]));
+            const F be = add(mul(vs[0][0], vi.m[0][1]), mul(vs[0][1], vi.m[1][1]));
+            put_mont(tbl, L::FB_ENTRY + 0, al);
+            put_mont(tbl, L::FB_ENTRY + 1, be);
+            put_v(tbl, L::FB_ENTRY + 2, sub(ks[0], add(mul(al, ks[1]), mul(be, ks[2]))));
+        }
+        // pair 0 reads Q = (F1, u_1, z_0, F2): a_0 = F1 + (v_1.w_0) z_0 ; b_0 = F2 + (v_2.w_0) z_0
+        F ha[4] = {one(), zero(), dot2(&vs[1][0], ws[0]), zero()}, ka = zero();
+        F hb[4] = {zero(), zero(), dot2(&vs[2][0], ws[0]), one()}, kb = zero();
+        const int n_pairs = rp / 2;
+        for (int p = 0; p < n_pairs; p++) {
+            const int a = 2 * p + 1, b = 2 * p + 2, base = L::FB_PART + p * L::FB_STRIDE;
+            const F c = dot2(&vs[b][0], ws[a]);
+            for (int x = 0; x < 4; x++) {
+                put_mont(tbl, base + L::FB_HA + x, ha[x]);
+                put_mont(tbl, base + L::FB_HB + x, hb[x]);
+            }
+            put_v(tbl, base + L::FB_KA, ka);
+            put_mont(tbl, base + L::FB_HB + 4, c);
+            put_v(tbl, base + L::FB_KB, kb);
+            const M2 vi = inv2(vs[a], vs[b]);
             for (int r = 0; r < 2; r++) {
-                const F* f = fn[r]->f;
-                const F g0 = add(mul(f[0], vi[0][0]), mul(f[1], vi[1][0]));
-                const F g1 = add(mul(f[0], vi[0][1]), mul(f[1], vi[1][1]));
-                put_mont(tbl, base + g_at[r] + 0, g0);
-                put_mont(tbl, base + g_at[r] + 1, g1);
-                put_mont(tbl, base + g_at[r] + 2, add(mul(f[0], ws[a][0]), mul(f[1], ws[a][1])));
-                put_mont(tbl, base + g_at[r] + 3, add(mul(f[0], ws[b][0]), mul(f[1], ws[b][1])));
-                put_v(tbl, base + k_at[r], sub(fn[r]->c, add(mul(g0, ks[a]), mul(g1, ks[b]))));
+                F f[2], cst;
+                if (p + 1 < n_pairs) {
+                    f[0] = vs[a + 2 + r][0], f[1] = vs[a + 2 + r][1], cst = ks[a + 2 + r];
+                } else {
+                    f[0] = r == 0 ? one() : zero(), f[1] = r == 0 ? zero() : one(), cst = D[1 + r];
+                }
+                const F g0 = add(mul(f[0], vi.m[0][0]), mul(f[1], vi.m[1][0]));
+                const F g1 = add(mul(f[0], vi.m[0][1]), mul(f[1], vi.m[1][1]));
+                F* h = r == 0 ? ha : hb;
+                h[0] = g0;
+                h[1] = g1;                                                    // b = u' - z_b - c z_a
+                h[2] = sub(dot2(f, ws[a]), mul(c, g1));
+                h[3] = sub(dot2(f, ws[b]), g1);
+                (r == 0 ? ka : kb) = sub(cst, add(mul(g0, ks[a]), mul(g1, ks[b])));
             }
         }
-        if (rp % 2) {
-            const int j = rp - 1;
-            if (vs[j][0].is_zero()) throw std::runtime_error("zero pivot in the last functional-basis round");
-            const F i0 = inv(vs[j][0]);
-            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 0, i0);
-            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 1, sub(zero(), mul(vs[j][1], i0)));
-            put_mont(tbl, L::FB_LAST + L::FB_L_G1 + 2, ws[j][0]);
-            put_v(tbl, L::FB_LAST + L::FB_L_K1, sub(D[1], mul(ks[j], i0)));
-            put_mont(tbl, L::FB_LAST + L::FB_L_W2, ws[j][1]);
-            put_v(tbl, L::FB_LAST + L::FB_L_D2, D[2]);
+        for (int x = 0; x < 4; x++) {
+            put_mont(tbl, L::FB_EXIT + L::FB_X_H1 + x, ha[x]);
+            put_mont(tbl, L::FB_EXIT + L::FB_X_H2 + x, hb[x]);
         }
+        put_v(tbl, L::FB_EXIT + L::FB_X_K1, ka);
+        put_v(tbl, L::FB_EXIT + L::FB_X_K2, kb);
     }
     {
         // round 0 on unconverted inputs (Layout::R0_M): M R^6, (C_0[0])^5 / R^4, C_0 canonical.

@@ -105,27 +105,29 @@ struct Layout {
     // c_j = v'_j . w'_{j-1} for every partial round j (c_0 = 0): lets the warp-cooperative
     // kernel (coop.cuh) form v'_j . s[1..] from the state of one round earlier
     static constexpr int COOP_C = OUT_ROW_MONT + T;      // [RP]
-    // Functional basis (width 3 only; derive_fb in tests/opt_model.py).  The two passive state
-    // elements are carried as the two functionals the NEXT pair of rounds reads,
-    //     a = v'_A . s[1..] + k'_A ,   b = v'_B . s[1..] + k'_B ,
-    // which a two-dimensional s[1..] is determined by, so a pair of rounds becomes
-    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a
-    //     a' = ga . (a, b, z_a, z_b) + ka ;  b' = gb . (a, b, z_a, z_b) + kb
-    // 9 products and 3 reductions instead of 9 and 4 (-4.6 % multiply-pipe instructions per
-    // pair).  For wider states the coordinate change costs more than the reduction it saves.
+    // Width 3 only (derive_fb / derive_fb2 in tests/opt_model.py).  The two passive state elements
+    // are a two-dimensional quantity, so they are determined by the two functionals the NEXT pair of
+    // rounds reads, a = v'_A . s[1..] + k'_A and b = v'_B . s[1..] + k'_B, and a pair becomes
+    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a .
+    // b is only ever added, so it never has to exist as a reduced value: with b = u' - z_b - c z_a the
+    // next pair's rows are rows over Q = (a, u', z_a, z_b), four values that exist anyway,
+    //     a' = ha . Q + ka ;   b' + c' z_a' = (hb, c') . (Q, z_a') + kb       (once z_a' is known)
+    // 9 products and 2 reductions per pair beside the two S-boxes, instead of 9 and 4 (-9 %
+    // multiply-pipe instructions per pair).  RP = 57 is odd: the odd round goes first, in the plain
+    // form.  For wider states the coordinate change costs more products than the reductions it saves.
     // The per-thread kernels use these records; the warp-cooperative schedule keeps the ones above.
     static constexpr bool FB = fb_rounds(T);
-    static constexpr int FB_PRE_M = COOP_C + RP;         // [T][T] rows 1, 2 of PRE_M mapped to (a_0, b_0)
-    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_0, k'_1)
-    static constexpr int FB_PART = FB_PRE_V + T;         // RP/2 records: c, ga[4], ka, gb[4], kb
+    static constexpr int FB_PRE_M = COOP_C + RP;         // [T][T] rows 1, 2 of PRE_M mapped to (F1, F2) = v'_{1,2} . s[1..]
+    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_1, k'_2)
+    static constexpr int FB_ENTRY = FB_PRE_V + T;        // al, be, k: u_1 = z_0 + al F1 + be F2 + k
+    static constexpr int FB_PART = FB_ENTRY + 3;         // RP/2 records: ha[4], ka, hb[4], c, kb
     static constexpr int FB_STRIDE = 11;
-    static constexpr int FB_C = 0, FB_GA = 1, FB_KA = 5, FB_GB = 6, FB_KB = 10;
-    // odd RP, the last round: s_1 = g1 . (a, b, z) + k1 ; s_2 = b + w2 z + d2 (constants D folded in)
-    static constexpr int FB_LAST = FB_PART + (RP / 2) * FB_STRIDE;
-    static constexpr int FB_L_G1 = 0, FB_L_K1 = 3, FB_L_W2 = 4, FB_L_D2 = 5, FB_L_COUNT = 6;
+    static constexpr int FB_HA = 0, FB_KA = 4, FB_HB = 5, FB_KB = 10;
+    static constexpr int FB_EXIT = FB_PART + (RP / 2) * FB_STRIDE;   // h1[4], k1, h2[4], k2: the plain s[1], s[2] (+ D)
+    static constexpr int FB_X_H1 = 0, FB_X_K1 = 4, FB_X_H2 = 5, FB_X_K2 = 9, FB_X_COUNT = 10;
     // (C_0[0])^5: what the first S-box makes of state[0] when the domain tag is zero (every circom
     // hasher, every tree node) -- a constant, so round 0 takes it from here instead of computing it
-    static constexpr int X0 = FB ? FB_LAST + (RP % 2) * FB_L_COUNT : COOP_C + RP;
+    static constexpr int X0 = FB ? FB_EXIT + FB_X_COUNT : COOP_C + RP;
     // Round 0 of the per-thread kernels runs on the inputs as they arrive, x + C_0 as a plain integer
     // (absorb_raw) instead of (x + C_0) R: the S-box then yields s^5 / R^4, and the round's matrix
     // carries the missing R^5 (R0_M = M R^6 against FULL_M = M R), so no input pays a conversion
@@ -199,46 +201,45 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     }
 
     if constexpr (L::FB) {
-        // ---- partial rounds, functional basis (Layout::FB): s = (u, a, b) ------------------
-        // q = (a, b, z_a, z_b), contiguous for the four-term rows.  Ranges: a, b < 2p + eps (range
-        // step of their rows), z < 1.7 p, so n = z_a + a and u' = z_b + (b + c z_a) are below 3.7 p
-        // before their range steps, and b + c z_a < 2p + 1.33 p.
-        static_assert(!L::FB || T == 3, "functional basis is derived for width 3");
-        uint32_t q[4][8];
+        // ---- partial rounds, width 3 (Layout::FB): round 3 left s = (u_0, F1, F2) ---------------
+        // q = (a, u, z_a of the previous pair, z_b of the previous pair, z_a), contiguous for the
+        // four- and five-term rows.  Ranges: a, u, F < 2p + eps (range steps), z < 1.7 p; the five-term
+        // row is below (0.189 * 9.4 + 1) p = 2.8 p before its range step; the sums z + row are below
+        // 3.7 p before theirs.
+        static_assert(!L::FB || (T == 3 && L::RP % 2 == 1), "derived for width 3 (odd round count)");
+        uint32_t q[5][8];
+        {
+            const uint32_t* pt = tbl + L::FB_ENTRY * 8;
+            uint32_t a[8];
+            sbox(q[2], s[0]);                                                   // z_0
+            dot<2, 8, true>(a, &s[1][0], pt, pt + 2 * 8);
+            add8(q[1], q[2], a);                                                // u_1
+            csub2p(q[1]);
 #pragma unroll
-        for (int k = 0; k < 8; k++) q[0][k] = s[1][k], q[1][k] = s[2][k];
+            for (int k = 0; k < 8; k++) q[0][k] = s[1][k], q[3][k] = s[2][k];
+        }
 #pragma unroll 1
         for (int j = 0; j < L::RP / 2; j++) {
             const uint32_t* pt = tbl + (L::FB_PART + j * L::FB_STRIDE) * 8;
-            uint32_t n[8], m[8], na[8];
+            uint32_t n[8], na[8], tt[8];
             INF_LOCKSTEP_SYNC();
-            sbox(q[2], s[0]);                                                   // z_a = u^5
-            add8(n, q[2], q[0]);
+            sbox(q[4], q[1]);                                                   // z_a = u^5
+            dot<4, 8, true>(na, &q[0][0], pt + L::FB_HA * 8, pt + L::FB_KA * 8);    // a
+            dot<5, 8, true>(tt, &q[0][0], pt + L::FB_HB * 8, pt + L::FB_KB * 8);    // b + c z_a
+            add8(n, q[4], na);
             csub2p(n);
-            mont_mul(m, q[2], pt + L::FB_C * 8);                                // b + c z_a
-            add8(m, m, q[1]);
-            csub2p(m);
             sbox(q[3], n);                                                      // z_b = n^5
-            add8(s[0], q[3], m);
-            csub2p(s[0]);
-            dot<4, 8, true>(na, &q[0][0], pt + L::FB_GA * 8, pt + L::FB_KA * 8);
-            dot<4, 8, true>(q[1], &q[0][0], pt + L::FB_GB * 8, pt + L::FB_KB * 8);   // reads q[1] before writing it: see dot
+            add8(q[1], q[3], tt);                                               // u'
+            csub2p(q[1]);
 #pragma unroll
-            for (int k = 0; k < 8; k++) q[0][k] = na[k];
+            for (int k = 0; k < 8; k++) q[0][k] = na[k], q[2][k] = q[4][k];
         }
-        if constexpr (L::RP % 2 == 1) {
-            const uint32_t* pt = tbl + L::FB_LAST * 8;
-            uint32_t w[8];
-            sbox(q[2], s[0]);
-            add8(s[0], q[2], q[0]);
-            csub2p(s[0]);
-            dot<3, 8, true>(s[1], &q[0][0], pt + L::FB_L_G1 * 8, pt + L::FB_L_K1 * 8);
-            mont_mul_add(w, q[2], pt + L::FB_L_W2 * 8, pt + L::FB_L_D2 * 8);
-            add8(s[2], q[1], w);
-            csub2p(s[2]);
-        } else {
+        {
+            const uint32_t* pt = tbl + L::FB_EXIT * 8;
+            dot<4, 8, true>(s[1], &q[0][0], pt + L::FB_X_H1 * 8, pt + L::FB_X_K1 * 8);
+            dot<4, 8, true>(s[2], &q[0][0], pt + L::FB_X_H2 * 8, pt + L::FB_X_K2 * 8);
 #pragma unroll
-            for (int k = 0; k < 8; k++) s[1][k] = q[0][k], s[2][k] = q[1][k];
+            for (int k = 0; k < 8; k++) s[0][k] = q[1][k];
         }
     } else {
     // ---- partial rounds -----------------------------------------------------

@@ -307,3 +307,94 @@ def hash_opt_fb(inputs, tag=0, tables=None, fb=None):
         if r + 1 < 8 + rp:
             s = [(x + y) % P for x, y in zip(s, C[r + 1])]
     return s[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# Width 3, rows over values that exist anyway (Layout<3>::FB, the form the kernels run)
+# ---------------------------------------------------------------------------------------------
+def derive_fb2(t=3, tables=None):
+    """derive_fb with b eliminated.  In a pair of rounds (A, B)
+        z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a
+    b is only ever ADDED, so it need not exist as a reduced value: with b = u' - z_b - c z_a the
+    next pair's two rows become rows over Q = (a, u', z_a, z_b), four values that exist anyway,
+        a'            = ha . Q + ka
+        b' + c' z_a'  = hb . Q + c' z_a' + kb        (one five-term row, once z_a' is known)
+    i.e. 9 products and 2 reductions per pair next to the two S-boxes.  The odd round (RP = 57)
+    goes first, in the plain form: the merged round-3 matrix yields u_0 and F_i = v_i.rest + k_i
+    (i = 1, 2), u_1 = z_0 + al F1 + be F2 + k (v_0 = al v_1 + be v_2), and the first pair reads
+    Q = (F1, u_1, z_0, F2) through selector rows.  After the last pair two rows over Q return the
+    plain state elements (tail constants D folded in)."""
+    assert t == 3
+    T = tables or derive(t)
+    rp, sc, D, PRE = T["rp"], T["scaled"], T["D"], T["PRE"]
+    assert rp % 2 == 1
+    inv = lambda x: pow(x, P - 2, P)
+    dotp = lambda x, y: sum(a * b for a, b in zip(x, y)) % P
+
+    def inv2(r0, r1):
+        di = inv((r0[0] * r1[1] - r0[1] * r1[0]) % P)
+        return [[r1[1] * di % P, -r0[1] * di % P], [-r1[0] * di % P, r0[0] * di % P]]
+
+    (v0, w0, k0), (v1, _, k1), (v2, _, k2) = sc[0], sc[1], sc[2]
+    pre = [list(PRE[0]),
+           [(v1[0] * PRE[1][x] + v1[1] * PRE[2][x]) % P for x in range(3)],
+           [(v2[0] * PRE[1][x] + v2[1] * PRE[2][x]) % P for x in range(3)]]
+    pre_v = [T["k"][0], k1, k2]
+    Vi = inv2(v1, v2)
+    ab = [(v0[0] * Vi[0][x] + v0[1] * Vi[1][x]) % P for x in range(2)]          # v_0 = al v_1 + be v_2
+    entry = (ab, (k0 - ab[0] * k1 - ab[1] * k2) % P)
+    n_pairs = rp // 2
+    recs = []
+    # pair 0 reads Q = (F1, u_1, z_0, F2): a_0 = F1 + (v_1.w_0) z_0 ; b_0 = F2 + (v_2.w_0) z_0
+    ha, ka = [1, 0, dotp(v1, w0), 0], 0
+    hb, kb = [0, 0, dotp(v2, w0), 1], 0
+    for p in range(n_pairs):
+        A, B = 2 * p + 1, 2 * p + 2
+        (vA, wA, kA), (vB, wB, kB) = sc[A], sc[B]
+        c = dotp(vB, wA)
+        recs.append((ha, ka, hb, c, kb))
+        Vi = inv2(vA, vB)
+        if p + 1 < n_pairs:
+            targets = [(sc[A + 2][0], sc[A + 2][2]), (sc[B + 2][0], sc[B + 2][2])]
+        else:
+            targets = [([1, 0], D[1]), ([0, 1], D[2])]
+        rows = []
+        for f, const in targets:
+            g = [(f[0] * Vi[0][x] + f[1] * Vi[1][x]) % P for x in range(2)]
+            # g.(a, b) + (f.w_A) z_a + (f.w_B) z_b + const - g.(k_A, k_B), with b = u' - z_b - c z_a
+            rows.append(([g[0], g[1], (dotp(f, wA) - c * g[1]) % P, (dotp(f, wB) - g[1]) % P],
+                         (const - g[0] * kA - g[1] * kB) % P))
+        (ha, ka), (hb, kb) = rows
+    return dict(pre=pre, pre_v=pre_v, entry=entry, pairs=recs, exit=((ha, ka), (hb, kb)))
+
+
+def hash_opt_fb2(inputs, tag=0, tables=None, fb=None):
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    F = fb or derive_fb2(t, T)
+    rp, M, C = T["rp"], T["M"], T["C"]
+    sb = lambda x: pow(x, 5, P)
+    dotp = lambda x, y: sum(a * b for a, b in zip(x, y)) % P
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    u, f1, f2 = [(x + y) % P for x, y in zip(_matvec(F["pre"], [sb(x) for x in s]), F["pre_v"])]
+    z0 = sb(u)
+    u = (z0 + dotp(F["entry"][0], (f1, f2)) + F["entry"][1]) % P
+    Q = (f1, u, z0, f2)
+    for ha, ka, hb, c, kb in F["pairs"]:
+        za = sb(Q[1])
+        a = (dotp(ha, Q) + ka) % P
+        tt = (dotp(hb, Q) + c * za + kb) % P
+        n = (za + a) % P
+        zb = sb(n)
+        Q = (a, (zb + tt) % P, za, zb)
+    (h1, k1), (h2, k2) = F["exit"]
+    s1, s2 = (dotp(h1, Q) + k1) % P, (dotp(h2, Q) + k2) % P
+    s = _matvec(T["TAIL0"], [sb(Q[1]), sb(s1), sb(s2)])
+    s = [(x + y) % P for x, y in zip(s, C[4 + rp + 1])]
+    for r in range(4 + rp + 1, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(x + y) % P for x, y in zip(s, C[r + 1])]
+    return s[0]

@@ -180,25 +180,28 @@ def test_library_optimised_tables_equal_python_derivation(emu, t):
     for j in range(rp):
         exp = 0 if j == 0 else sum(a * b for a, b in zip(T["scaled"][j][0], T["scaled"][j - 1][1])) % P
         assert el(k) == mont(exp); k += 1
-    if t == 3:                                   # functional-basis records (Layout<3>::FB)
-        F = opt_model.derive_fb(t, T)
+    if t == 3:                                   # rows over Q = (a, u', z_a, z_b) (Layout<3>::FB)
+        F = opt_model.derive_fb2(t, T)
         for row in F["pre"]:
             for x in row:
                 assert el(k) == mont(x); k += 1
         for x in F["pre_v"]:
             assert el(k) == vform(x); k += 1
-        for c, (ga, ka), (gb, kb) in F["pairs"]:
+        assert el(k) == mont(F["entry"][0][0]); k += 1
+        assert el(k) == mont(F["entry"][0][1]); k += 1
+        assert el(k) == vform(F["entry"][1]); k += 1
+        for ha, ka, hb, c, kb in F["pairs"]:
+            for x in ha:
+                assert el(k) == mont(x); k += 1
+            assert el(k) == vform(ka); k += 1
+            for x in hb:
+                assert el(k) == mont(x); k += 1
             assert el(k) == mont(c); k += 1
-            for g, kk in ((ga, ka), (gb, kb)):
-                for x in g:
-                    assert el(k) == mont(x); k += 1
-                assert el(k) == vform(kk); k += 1
-        L = F["last"]
-        for x in L["g1"]:
-            assert el(k) == mont(x); k += 1
-        assert el(k) == vform(L["k1"]); k += 1
-        assert el(k) == mont(L["w2"]); k += 1
-        assert el(k) == vform(L["d2"]); k += 1
+            assert el(k) == vform(kb); k += 1
+        for h, kk in F["exit"]:
+            for x in h:
+                assert el(k) == mont(x); k += 1
+            assert el(k) == vform(kk); k += 1
     # round 0 on unconverted inputs: X0 = (C_0[0])^5 / R^4, R0_M = M R^6, IN_C = C_0
     assert el(k) == pow(T["C"][0][0], 5, P) * pow(R, -4, P) % P; k += 1
     for i in range(t):

@@ -51,3 +51,15 @@ def test_functional_basis_schedule_equals_dense():
         ins = [rng.randrange(O.P) for _ in range(2)]
         tag = 0 if i % 3 else rng.randrange(O.P)
         assert opt_model.hash_opt_fb(ins, tag, T, F) == O.poseidon_permute_hash(ins, tag)
+
+
+def test_rows_over_existing_values_schedule_equals_dense():
+    """Width 3 as the kernels run it: b eliminated, rows over Q = (a, u', z_a, z_b), odd round first."""
+    T = opt_model.derive(3)
+    F = opt_model.derive_fb2(3, T)
+    assert len(F["pairs"]) == 28
+    rng = random.Random(34)
+    for i in range(12):
+        ins = [rng.randrange(O.P) for _ in range(2)]
+        tag = 0 if i % 3 else rng.randrange(O.P)
+        assert opt_model.hash_opt_fb2(ins, tag, T, F) == O.poseidon_permute_hash(ins, tag)
