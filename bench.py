@@ -636,10 +636,10 @@ def run_ours(args, rank, world, local_rank):
         ex["pipe_bound_hashes_per_s"] = sms * 4 * sm_max_mhz * 1e6 / cyc * 32   # the multiply pipe never idle
         return ex
 
-    ex3 = executed_of("poseidon_t3.o", "hash_batch_kernelILb0", [4, 28, 3], {"imad_wide": 51281, "imad_hi": 2808, "imad": 2808})
-    ex3t = executed_of("poseidon_t3.o", "tree_level_kernel", [4, 28, 3], {"imad_wide": 51281, "imad_hi": 2808, "imad": 2808})
-    ex6 = executed_of("poseidon_t6.o", "hash_batch_kernelILb0", [4, 30, 3], {"imad_wide": 103834, "imad_hi": 4616, "imad": 4617})
-    ex6t = executed_of("poseidon_t6.o", "tree_level_kernel", [4, 30, 3], {"imad_wide": 103834, "imad_hi": 4616, "imad": 4617})
+    ex3 = executed_of("poseidon_t3.o", "hash_batch_kernelILb0", [4, 55, 3], {"imad_wide": 48601, "imad_hi": 2616, "imad": 2616})
+    ex3t = executed_of("poseidon_t3.o", "tree_level_kernel", [4, 55, 3], {"imad_wide": 48601, "imad_hi": 2616, "imad": 2616})
+    ex6 = executed_of("poseidon_t6.o", "hash_batch_kernelILb0", [4, 55, 3], {"imad_wide": 95378, "imad_hi": 3480, "imad": 3481})
+    ex6t = executed_of("poseidon_t6.o", "tree_level_kernel", [4, 55, 3], {"imad_wide": 95378, "imad_hi": 3480, "imad": 3481})
     rate = n / (avg_launch_ms * 1e-3)
     ex3.update({"frac_of_pipe_bound": rate / ex3["pipe_bound_hashes_per_s"],
                 "wide_per_s": ex3["imad_wide"] * rate / 1e12,

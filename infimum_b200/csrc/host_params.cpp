@@ -255,6 +255,55 @@ std::vector<uint32_t> build_opt(void) {
         put_mont(tbl, L::COOP_C + j, c);
     }
     for (int i = 1; i < T; i++) put_mont(tbl, L::LAST_D + i - 1, D[i]);
+    if constexpr (L::HR) {
+        // history recurrence (Layout::HR; derive_hr in tests/opt_model.py)
+        const int n = T - 1;
+        auto dotv = [&](const std::vector<F>& x, const std::vector<F>& y) {
+            F acc = zero();
+            for (int i = 0; i < n; i++) acc = add(acc, mul(x[i], y[i]));
+            return acc;
+        };
+        for (int c = 0; c < T; c++) put_mont(tbl, L::HR_PRE_M + c, PRE[c]);
+        for (int j = 0; j < n; j++)
+            for (int c = 0; c < T; c++) {
+                F acc = zero();
+                for (int x = 0; x < n; x++) acc = add(acc, mul(vs[j][x], PRE[(1 + x) * T + c]));
+                put_mont(tbl, L::HR_PRE_M + (1 + j) * T + c, acc);
+            }
+        put_v(tbl, L::HR_PRE_V + 0, k[0]);
+        for (int j = 0; j < n; j++) put_v(tbl, L::HR_PRE_V + 1 + j, ks[j]);
+        for (int j = 1; j < n; j++)
+            for (int i = j - 1; i >= 0; i--)                       // newest z first
+                put_mont(tbl, L::HR_BOOT + j * (j - 1) / 2 + (j - 1 - i), dotv(vs[j], ws[i]));
+        // row for a functional f (constant kf) of the passive state at round j, over
+        // (u_j, .., u_{j-n+1}; z_{j-1}, .., z_{j-n})
+        auto put_row = [&](int base, int j, const std::vector<F>& f, const F& kf) {
+            Mat A(n * n);
+            for (int i = 1; i <= n; i++)
+                for (int x = 0; x < n; x++) A[(i - 1) * n + x] = vs[j - i][x];
+            const Mat Ai = matinv(A, n);
+            std::vector<F> g(n, zero());                           // f . A^-1
+            for (int i = 0; i < n; i++)
+                for (int x = 0; x < n; x++) g[i] = add(g[i], mul(f[x], Ai[x * n + i]));
+            F cst = kf;
+            for (int i = 1; i <= n; i++) {
+                put_mont(tbl, base + i - 1, g[i - 1]);
+                cst = sub(cst, mul(g[i - 1], ks[j - i]));
+            }
+            for (int l = 1; l <= n; l++) {
+                F be = neg(g[l - 1]);
+                for (int i = l; i <= n; i++) be = add(be, mul(g[i - 1], dotv(vs[j - i], ws[j - l])));
+                put_mont(tbl, base + n + l - 1, be);
+            }
+            put_v(tbl, base + 2 * n, cst);
+        };
+        for (int j = n; j < rp; j++) put_row(L::HR_PART + (j - n) * L::HR_STRIDE, j, vs[j], ks[j]);
+        for (int i = 0; i < n; i++) {
+            std::vector<F> e(n, zero());
+            e[i] = one();
+            put_row(L::HR_EXIT + i * L::HR_STRIDE, rp, e, D[1 + i]);
+        }
+    }
     if constexpr (L::FB) {
         // width 3: rows over Q = (a, u', z_a, z_b) (Layout::FB; derive_fb2 in tests/opt_model.py)
         static_assert(!L::FB || T == 3, "derived for width 3");

@@ -18,8 +18,8 @@
 namespace inf {
 namespace {
 
-__constant__ uint32_t c_tbl5[Layout<5>::WORDS];
-__constant__ uint32_t c_tbl6[Layout<6>::WORDS];
+__constant__ uint32_t c_tbl5[Layout<5>::THREAD_WORDS];   // the per-thread kernels' prefix of the table
+__constant__ uint32_t c_tbl6[Layout<6>::THREAD_WORDS];
 
 __device__ __forceinline__ void load_node(uint32_t (&w)[8], const uint4* p) {
     const uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -117,9 +117,9 @@ cudaError_t upload_leaf_tables(const uint32_t* t5, size_t w5, const uint32_t* t6
     if (w5 != (size_t)Layout<5>::WORDS || w6 != (size_t)Layout<6>::WORDS) return cudaErrorInvalidValue;
     leaf_block(1);          // settle the lazily read overrides and the per-device SM count here, under inf_init's lock
     leaf_sms();
-    cudaError_t e = cudaMemcpyToSymbol(c_tbl5, t5, w5 * 4);
+    cudaError_t e = cudaMemcpyToSymbol(c_tbl5, t5, (size_t)Layout<5>::THREAD_WORDS * 4);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_tbl6, t6, w6 * 4);
+    return cudaMemcpyToSymbol(c_tbl6, t6, (size_t)Layout<6>::THREAD_WORDS * 4);
 }
 
 cudaError_t launch_interaction_leaves(const void* d_pk, const void* d_data, void* d_out, uint64_t n,

@@ -70,24 +70,96 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 // plain sparse form, and nothing but an addition between one S-box and the next.
 // The scale comes off in the first round of the second half, whose matrix has
 // column 0 multiplied by lambda_RP^5 (TAIL0_M).
-// Widths whose per-thread kernels run the partial rounds in the functional basis (Layout::FB).
+//
+// Three forms of the partial section live in the table (all exact rewritings of the same map):
+//   * the history recurrence (HR, widths 2..6; what the per-thread kernels run),
+//   * width 3's rows over Q (FB; built only without HR, -DINF_NO_HR),
+//   * the paired sparse rounds (widths 7, 8, and every width's warp-cooperative schedule, coop.cuh).
+
+// History recurrence (derive_hr in tests/opt_model.py).  The passive state s[1..] (n = T-1 elements) is
+// only ever read through row functionals, and the n equations
+//     u_{j+1-i} = z_{j-i} + v'_{j-i} . s[1..]^(j-i) + k'_{j-i}        (i = 1..n)
+// determine it from S-box inputs u and outputs z, values that exist anyway.  So a partial round is
+//     z_j = u_j^5 ;   u_{j+1} = z_j + sum_{i=1..n} ( al_i u_{j+1-i} + be_i z_{j-i} ) + const :
+// 2n products and ONE reduction beside the S-box and nothing else to update, against 2n + 1/2 products
+// and (n + 2)/2 reductions per round of the paired sparse form (-12 % multiply-pipe instructions per
+// hash5, -11 % per hash2).  The first n rounds read their rows F_j = v'_j . s[1..]^(0) + k'_j straight
+// out of the merged round-3 matrix plus the few z that exist by then; after the last round n rows over
+// the same history return the plain s[1..] (constants D folded in).  The widest row sums 2n terms:
+// bounded by (0.189 (2n + 1.7n) + 1) p = 4.5 p < 2^256 for n = 5; widths 7 and 8 would overflow.
+#ifdef INF_NO_HR
+INF_HD constexpr bool hr_rounds(int) { return false; }
+#else
+INF_HD constexpr bool hr_rounds(int t) { return t >= 2 && t <= 6; }
+#endif
+// Width 3's rows over Q (Layout::FB), kept as the alternative to HR.
 #ifdef INF_NO_FB
 INF_HD constexpr bool fb_rounds(int) { return false; }
 #else
-INF_HD constexpr bool fb_rounds(int t) { return t == 3; }
+INF_HD constexpr bool fb_rounds(int t) { return t == 3 && !hr_rounds(t); }
+#endif
+#ifndef INF_HR_UNROLL
+#define INF_HR_UNROLL 1      // rounds per loop body: 1 shifts the history with register moves, n renames them away
 #endif
 
 template <int T>
 struct Layout {
     static constexpr int RP = partial_rounds(T);
+    static constexpr int N = T - 1;
+    // ---- every schedule -------------------------------------------------------------------------
     static constexpr int R2 = 0;                         // R^2 mod p
     static constexpr int IN_V = R2 + 1;                  // [T]   C_0[i] * R^2
     static constexpr int S0 = IN_V + T;                  // C_0[0] * R   (state[0] when tag == 0)
     static constexpr int FULL_M = S0 + 1;                // [T][T] MDS
-    static constexpr int PRE_M = FULL_M + T * T;         // [T][T] MDS with the sparse prefix merged
-    static constexpr int TAIL0_M = PRE_M + T * T;        // [T][T] MDS, column 0 times lambda_RP^5
+    static constexpr int TAIL0_M = FULL_M + T * T;       // [T][T] MDS, column 0 times lambda_RP^5
     static constexpr int FULL_V = TAIL0_M + T * T;       // [3][T] C_{r+1}, r = 0..2
-    static constexpr int PRE_V = FULL_V + 3 * T;         // [T]   (k_0, 0, ..., 0)
+    static constexpr int TAIL_V = FULL_V + 3 * T;        // [3][T] C_{4+RP+r+1}, r = 0..2
+    static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
+    static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
+    // (C_0[0])^5: what the first S-box makes of state[0] when the domain tag is zero (every circom
+    // hasher, every tree node) -- a constant, so round 0 takes it from here instead of computing it
+    static constexpr int X0 = OUT_ROW_MONT + T;
+    // Round 0 of the per-thread kernels runs on the inputs as they arrive, x + C_0 as a plain integer
+    // (absorb_raw) instead of (x + C_0) R: the S-box then yields s^5 / R^4, and the round's matrix
+    // carries the missing R^5 (R0_M = M R^6 against FULL_M = M R), so no input pays a conversion
+    // product.  X0 is stored in the same scale, (C_0[0])^5 / R^4.  IN_C = C_0 as canonical integers.
+    static constexpr int R0_M = X0 + 1;                  // [T][T]
+    static constexpr int IN_C = R0_M + T * T;            // [T]
+    static constexpr int COMMON_END = IN_C + T;
+    // ---- history recurrence ------------------------------------------------------------------------
+    static constexpr bool HR = hr_rounds(T);
+    static constexpr int HR_PRE_M = COMMON_END;          // [T][T] row 1 + j of PRE_M mapped to F_j
+    static constexpr int HR_PRE_V = HR_PRE_M + T * T;    // [T]    (k_0, k'_0, .., k'_{n-1})
+    // rounds j = 1..n-1: c_{j,i} = v'_j . w'_i for i = j-1 .. 0 (newest z first), at HR_BOOT + j(j-1)/2
+    static constexpr int HR_BOOT = HR_PRE_V + T;
+    // rounds j = n..RP-1: al[n] (u_j, u_{j-1}, ..), be[n] (z_{j-1}, z_{j-2}, ..), const
+    static constexpr int HR_PART = HR_BOOT + N * (N - 1) / 2;
+    static constexpr int HR_STRIDE = 2 * N + 1;
+    static constexpr int HR_ROUNDS = RP - N;
+    static constexpr int HR_EXIT = HR_PART + HR_ROUNDS * HR_STRIDE;   // n rows at j = RP: the plain s[1..] (+ D)
+    static constexpr int HR_END = HR ? HR_EXIT + N * HR_STRIDE : COMMON_END;
+    // ---- width 3, rows over Q (derive_fb2 in tests/opt_model.py) ----------------------------------
+    // The two passive state elements are determined by the two functionals the NEXT pair of rounds
+    // reads, a = v'_A . s[1..] + k'_A and b = v'_B . s[1..] + k'_B, and a pair becomes
+    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a .
+    // b is only ever added, so it never has to exist as a reduced value: with b = u' - z_b - c z_a the
+    // next pair's rows are rows over Q = (a, u', z_a, z_b), four values that exist anyway,
+    //     a' = ha . Q + ka ;   b' + c' z_a' = (hb, c') . (Q, z_a') + kb       (once z_a' is known)
+    // 9 products and 2 reductions per pair beside the two S-boxes, instead of 9 and 4.  RP = 57 is odd:
+    // the odd round goes first, in the plain form.
+    static constexpr bool FB = fb_rounds(T);
+    static constexpr int FB_PRE_M = HR_END;              // [T][T] rows 1, 2 of PRE_M mapped to (F1, F2) = v'_{1,2} . s[1..]
+    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_1, k'_2)
+    static constexpr int FB_ENTRY = FB_PRE_V + T;        // al, be, k: u_1 = z_0 + al F1 + be F2 + k
+    static constexpr int FB_PART = FB_ENTRY + 3;         // RP/2 records: ha[4], ka, hb[4], c, kb
+    static constexpr int FB_STRIDE = 11;
+    static constexpr int FB_HA = 0, FB_KA = 4, FB_HB = 5, FB_KB = 10;
+    static constexpr int FB_EXIT = FB_PART + (RP / 2) * FB_STRIDE;   // h1[4], k1, h2[4], k2: the plain s[1], s[2] (+ D)
+    static constexpr int FB_X_H1 = 0, FB_X_K1 = 4, FB_X_H2 = 5, FB_X_K2 = 9, FB_X_COUNT = 10;
+    static constexpr int FB_END = FB ? FB_EXIT + FB_X_COUNT : HR_END;
+    // ---- paired sparse rounds ----------------------------------------------------------------------
+    static constexpr int PRE_M = FB_END;                 // [T][T] MDS with the sparse prefix merged
+    static constexpr int PRE_V = PRE_M + T * T;          // [T]   (k_0, 0, ..., 0)
     static constexpr bool PAIRED = paired_rounds(T);
     // single round record [2T-1] : v'[T-1], w'[T-1], k'
     // pair record        [4T-1] : v'_A[T-1], k'_A, v'_B[T-1], c_B, k'_B, (w'_A[i], w'_B[i]) for i = 1..T-1
@@ -99,43 +171,15 @@ struct Layout {
     static constexpr int N_SINGLES = PAIRED ? RP % 2 : RP;
     static constexpr int SINGLES = PART + N_PAIRS * PAIR_STRIDE;
     static constexpr int LAST_D = SINGLES + N_SINGLES * SINGLE_STRIDE;   // [T-1]  D[1..] * R (added once)
-    static constexpr int TAIL_V = LAST_D + (T - 1);      // [3][T] C_{4+RP+r+1}, r = 0..2
-    static constexpr int OUT_ROW = TAIL_V + 3 * T;       // [T]   MDS row 0, canonical
-    static constexpr int OUT_ROW_MONT = OUT_ROW + T;     // [T]   MDS row 0, Montgomery (chaining)
     // c_j = v'_j . w'_{j-1} for every partial round j (c_0 = 0): lets the warp-cooperative
     // kernel (coop.cuh) form v'_j . s[1..] from the state of one round earlier
-    static constexpr int COOP_C = OUT_ROW_MONT + T;      // [RP]
-    // Width 3 only (derive_fb / derive_fb2 in tests/opt_model.py).  The two passive state elements
-    // are a two-dimensional quantity, so they are determined by the two functionals the NEXT pair of
-    // rounds reads, a = v'_A . s[1..] + k'_A and b = v'_B . s[1..] + k'_B, and a pair becomes
-    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a .
-    // b is only ever added, so it never has to exist as a reduced value: with b = u' - z_b - c z_a the
-    // next pair's rows are rows over Q = (a, u', z_a, z_b), four values that exist anyway,
-    //     a' = ha . Q + ka ;   b' + c' z_a' = (hb, c') . (Q, z_a') + kb       (once z_a' is known)
-    // 9 products and 2 reductions per pair beside the two S-boxes, instead of 9 and 4 (-9 %
-    // multiply-pipe instructions per pair).  RP = 57 is odd: the odd round goes first, in the plain
-    // form.  For wider states the coordinate change costs more products than the reductions it saves.
-    // The per-thread kernels use these records; the warp-cooperative schedule keeps the ones above.
-    static constexpr bool FB = fb_rounds(T);
-    static constexpr int FB_PRE_M = COOP_C + RP;         // [T][T] rows 1, 2 of PRE_M mapped to (F1, F2) = v'_{1,2} . s[1..]
-    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_1, k'_2)
-    static constexpr int FB_ENTRY = FB_PRE_V + T;        // al, be, k: u_1 = z_0 + al F1 + be F2 + k
-    static constexpr int FB_PART = FB_ENTRY + 3;         // RP/2 records: ha[4], ka, hb[4], c, kb
-    static constexpr int FB_STRIDE = 11;
-    static constexpr int FB_HA = 0, FB_KA = 4, FB_HB = 5, FB_KB = 10;
-    static constexpr int FB_EXIT = FB_PART + (RP / 2) * FB_STRIDE;   // h1[4], k1, h2[4], k2: the plain s[1], s[2] (+ D)
-    static constexpr int FB_X_H1 = 0, FB_X_K1 = 4, FB_X_H2 = 5, FB_X_K2 = 9, FB_X_COUNT = 10;
-    // (C_0[0])^5: what the first S-box makes of state[0] when the domain tag is zero (every circom
-    // hasher, every tree node) -- a constant, so round 0 takes it from here instead of computing it
-    static constexpr int X0 = FB ? FB_EXIT + FB_X_COUNT : COOP_C + RP;
-    // Round 0 of the per-thread kernels runs on the inputs as they arrive, x + C_0 as a plain integer
-    // (absorb_raw) instead of (x + C_0) R: the S-box then yields s^5 / R^4, and the round's matrix
-    // carries the missing R^5 (R0_M = M R^6 against FULL_M = M R), so no input pays a conversion
-    // product.  X0 is stored in the same scale, (C_0[0])^5 / R^4.  IN_C = C_0 as canonical integers.
-    static constexpr int R0_M = X0 + 1;                  // [T][T]
-    static constexpr int IN_C = R0_M + T * T;            // [T]
-    static constexpr int COUNT = IN_C + T;
+    static constexpr int COOP_C = LAST_D + (T - 1);      // [RP]
+    static constexpr int COUNT = COOP_C + RP;
     static constexpr int WORDS = COUNT * 8;
+    // what the per-thread kernels read (a unit that only has those, leaves.cu, keeps just this prefix
+    // in its constant bank)
+    static constexpr int THREAD_COUNT = HR ? HR_END : FB ? FB_END : COUNT;
+    static constexpr int THREAD_WORDS = THREAD_COUNT * 8;
     // offsets inside a pair record
     static constexpr int P_VA = 0, P_KA = T - 1, P_VB = T, P_CB = 2 * T - 1, P_KB = 2 * T, P_W = 2 * T + 1;
     // offsets inside a single record
@@ -165,6 +209,39 @@ INF_HD void sbox(uint32_t (&y)[8], const uint32_t (&x)[8]) {
     mont_mul(y, x4, x);
 }
 
+// Range steps of a history-recurrence row (Layout::HR): below (0.7 n + 1) p on entry, below 2p + 2^224 on return.
+template <int N>
+INF_HD void hr_range(uint32_t (&v)[8]) {
+    if (N >= 5) csub4p(v);          // 0.7 n + 1 > 4: one step of 2p would leave up to 2.5 p
+    csub2p(v);
+}
+
+// Rounds 0..n-1 of the history recurrence: u_{J+1} = z_J + F_J + sum_{i<J} c_{J,i} z_i, with u_{J+1}
+// and z_J written where the steady rounds expect them once J = n-1 is through (h[n-1-J], h[2n-1-J]):
+// the z that exist so far are then contiguous, newest first, from h[2n-J].
+template <int T, int J>
+INF_HD void hr_boot(uint32_t (&h)[2 * (T - 1)][8], uint32_t (&s)[T][8], const uint32_t* tbl) {
+    using L = Layout<T>;
+    constexpr int N = T - 1;
+    if constexpr (J < N) {
+        uint32_t (&z)[8] = h[2 * N - 1 - J];
+        uint32_t (&u)[8] = h[N - 1 - J];
+        if constexpr (J == 0) {
+            sbox(z, s[0]);
+            add8(u, z, s[1]);
+        } else {
+            uint32_t v[8];
+            sbox(z, h[N - J]);                                                   // u_J
+            dot<J, 8, false>(v, &h[2 * N - J][0], tbl + (L::HR_BOOT + J * (J - 1) / 2) * 8, nullptr);
+            add8(v, v, s[1 + J]);                                                // < 2.3 p + 2p
+            csub2p(v);
+            add8(u, z, v);
+        }
+        csub2p(u);
+        hr_boot<T, J + 1>(h, s, tbl);
+    }
+}
+
 // The permutation proper.  On entry s = [tag, inputs...] + C_0 in Montgomery
 // form, every element < 2p + eps.  On return `out` holds state[0] after the
 // last round: canonical integer in [0, p) if !MONT_OUT, Montgomery form
@@ -185,8 +262,10 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     // ---- first half: rounds 0..3 (round 3 uses the merged matrix) ----------
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-        const uint32_t* m = tbl + (r == 0 && raw_in ? L::R0_M : r < 3 ? L::FULL_M : L::FB ? L::FB_PRE_M : L::PRE_M) * 8;
-        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : L::FB ? L::FB_PRE_V : L::PRE_V) * 8;
+        constexpr int PM = L::HR ? L::HR_PRE_M : L::FB ? L::FB_PRE_M : L::PRE_M;
+        constexpr int PV = L::HR ? L::HR_PRE_V : L::FB ? L::FB_PRE_V : L::PRE_V;
+        const uint32_t* m = tbl + (r == 0 && raw_in ? L::R0_M : r < 3 ? L::FULL_M : PM) * 8;
+        const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : PV) * 8;
         INF_LOCKSTEP_SYNC();
         if (r == 0 && tag0) {
 #pragma unroll
@@ -200,7 +279,41 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         for (int i = 0; i < T; i++) dot<T, 8, RS>(s[i], &x[0][0], m + i * T * 8, v + i * 8);
     }
 
-    if constexpr (L::FB) {
+    if constexpr (L::HR) {
+        // ---- partial rounds as a recurrence over the last n S-box inputs and outputs (Layout::HR) ----
+        // round 3 left s = (u_0, F_0, .., F_{n-1}).  h = (u_j, u_{j-1}, .., u_{j-n+1}; z_{j-1}, .., z_{j-n}).
+        // Ranges: u < 2p + eps and z < 1.7 p, so a row is below (0.189 * 3.7 n + 1) p -- 4.5 p for n = 5,
+        // under 2^256 = 5.29 p -- and below 2p + eps after its range steps; z + row < 3.7 p before its own.
+        constexpr int N = L::N;
+        constexpr int UNR = INF_HR_UNROLL;
+        uint32_t h[2 * N][8];
+        hr_boot<T, 0>(h, s, tbl);
+#pragma unroll UNR
+        for (int j = 0; j < L::HR_ROUNDS; j++) {
+            const uint32_t* pt = tbl + (L::HR_PART + j * L::HR_STRIDE) * 8;
+            uint32_t z[8], v[8];
+            INF_LOCKSTEP_SYNC();
+            sbox(z, h[0]);                                                      // z_j = u_j^5
+            dot<2 * N, 8, false>(v, &h[0][0], pt, pt + 2 * N * 8);
+            hr_range<N>(v);
+#pragma unroll
+            for (int i = N - 1; i > 0; i--)
+#pragma unroll
+                for (int k = 0; k < 8; k++) h[i][k] = h[i - 1][k], h[N + i][k] = h[N + i - 1][k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[N][k] = z[k];
+            add8(h[0], z, v);                                                   // u_{j+1}
+            csub2p(h[0]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t* pt = tbl + (L::HR_EXIT + i * L::HR_STRIDE) * 8;
+            dot<2 * N, 8, false>(s[1 + i], &h[0][0], pt, pt + 2 * N * 8);
+            hr_range<N>(s[1 + i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[0][k] = h[0][k];
+    } else if constexpr (L::FB) {
         // ---- partial rounds, width 3 (Layout::FB): round 3 left s = (u_0, F1, F2) ---------------
         // q = (a, u, z_a of the previous pair, z_b of the previous pair, z_a), contiguous for the
         // four- and five-term rows.  Ranges: a, u, F < 2p + eps (range steps), z < 1.7 p; the five-term

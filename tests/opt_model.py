@@ -398,3 +398,73 @@ def hash_opt_fb2(inputs, tag=0, tables=None, fb=None):
         if r + 1 < 8 + rp:
             s = [(x + y) % P for x, y in zip(s, C[r + 1])]
     return s[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# History recurrence (Layout<T>::HR): the partial rounds with NO state but the S-box inputs and
+# outputs of the last t-1 rounds
+# ---------------------------------------------------------------------------------------------
+def derive_hr(t, tables=None):
+    """The passive state rest (n = t-1 elements) is only ever read through row functionals, and the
+    n equations  u_{j+1-i} = z_{j-i} + v_{j-i}.rest^(j-i) + k_{j-i}  (i = 1..n) determine it from
+    S-box inputs u and outputs z that exist anyway as reduced values.  So every partial round is
+        z_j = u_j^5 ;  u_{j+1} = z_j + sum_{i=1..n} (al_i u_{j+1-i} + be_i z_{j-i}) + const
+    2n products and ONE reduction beside the S-box, with nothing else to update.  The first n rounds
+    read the functionals F_j = v_j.rest^(0) + k_j straight out of the merged round-3 matrix (row j+1
+    of PRE replaced by v_j.PRE[1:]) plus the few z that exist by then; after the last round n rows
+    over the same history return the plain state elements (tail constants D folded in).
+    Records: steady[j - n] = (al[n], be[n], const) for rounds j = n..RP-1, in the order
+    (u_j, u_{j-1}, ..; z_{j-1}, z_{j-2}, ..); exit rows likewise at j = RP."""
+    T = tables or derive(t)
+    rp, sc, D, PRE = T["rp"], T["scaled"], T["D"], T["PRE"]
+    n = t - 1
+    dotp = lambda x, y: sum(a * b for a, b in zip(x, y)) % P
+    pre = [list(PRE[0])] + [[dotp(sc[j][0], [PRE[1 + x][c] for x in range(n)]) for c in range(t)] for j in range(n)]
+    pre_v = [T["k"][0]] + [sc[j][2] for j in range(n)]
+    boot = [[dotp(sc[j][0], sc[i][1]) for i in range(j)] for j in range(n)]          # boot[j][i] = v_j . w_i
+
+    def row(j, f, kf):
+        A = [sc[j - i][0] for i in range(1, n + 1)]
+        Ai = _inv(A)
+        g = [sum(f[x] * Ai[x][i] for x in range(n)) % P for i in range(n)]           # f . A^-1
+        al = g
+        be = [(-g[l - 1] + sum(g[i - 1] * dotp(sc[j - i][0], sc[j - l][1]) for i in range(l, n + 1))) % P
+              for l in range(1, n + 1)]
+        const = (kf - sum(g[i - 1] * sc[j - i][2] for i in range(1, n + 1))) % P
+        return al, be, const
+
+    steady = [row(j, sc[j][0], sc[j][2]) for j in range(n, rp)]
+    unit = lambda i: [1 if x == i else 0 for x in range(n)]
+    exit_rows = [row(rp, unit(i), D[1 + i]) for i in range(n)]
+    return dict(n=n, pre=pre, pre_v=pre_v, boot=boot, steady=steady, exit=exit_rows)
+
+
+def hash_opt_hr(inputs, tag=0, tables=None, hr=None):
+    t = len(inputs) + 1
+    T = tables or derive(t)
+    H = hr or derive_hr(t, T)
+    rp, M, C, n = T["rp"], T["M"], T["C"], t - 1
+    sb = lambda x: pow(x, 5, P)
+    dotp = lambda x, y: sum(a * b for a, b in zip(x, y)) % P
+    s = [(a + b) % P for a, b in zip([tag % P] + [x % P for x in inputs], C[0])]
+    for r in range(3):
+        s = [(a + b) % P for a, b in zip(_matvec(M, [sb(x) for x in s]), C[r + 1])]
+    s = [(x + y) % P for x, y in zip(_matvec(H["pre"], [sb(x) for x in s]), H["pre_v"])]
+    us, zs = [s[0]], []                         # us[j] = u_j, zs[j] = z_j
+    for j in range(rp):
+        zs.append(sb(us[j]))
+        if j < n:
+            v = (s[1 + j] + dotp(H["boot"][j], zs[:j])) % P
+        else:
+            al, be, const = H["steady"][j - n]
+            v = (dotp(al, [us[j + 1 - i] for i in range(1, n + 1)]) + dotp(be, [zs[j - i] for i in range(1, n + 1)]) + const) % P
+        us.append((zs[j] + v) % P)
+    rest = [(dotp(al, [us[rp + 1 - i] for i in range(1, n + 1)]) + dotp(be, [zs[rp - i] for i in range(1, n + 1)]) + const) % P
+            for al, be, const in H["exit"]]
+    s = _matvec(T["TAIL0"], [sb(us[rp])] + [sb(x) for x in rest])
+    s = [(x + y) % P for x, y in zip(s, C[4 + rp + 1])]
+    for r in range(4 + rp + 1, 8 + rp):
+        s = _matvec(M, [sb(x) for x in s])
+        if r + 1 < 8 + rp:
+            s = [(x + y) % P for x, y in zip(s, C[r + 1])]
+    return s[0]

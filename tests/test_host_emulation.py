@@ -120,96 +120,73 @@ def test_library_grain_constants_equal_oracle(emu, t):
 
 @pytest.mark.parametrize("t", range(2, 9))
 def test_library_optimised_tables_equal_python_derivation(emu, t):
+    """Every entry of the table the library derives at init (host_params.cpp, Layout<T> in poseidon.cuh)
+    against the independent Python derivation, in table order."""
     T = opt_model.derive(t)
     words = emu.hostemu_opt_table_words(t)
     buf = (ctypes.c_uint32 * words)()
     assert emu.hostemu_opt_table(t, buf) == words
     el = lambda k: sum(int(buf[8 * k + i]) << (32 * i) for i in range(8))
-    rp = T["rp"]
+    rp, n = T["rp"], t - 1
     mont = lambda x: x * R % P
     vform = lambda x: x * R * R % P
-    k = 0
-    assert el(k) == R * R % P; k += 1
-    for i in range(t):
-        assert el(k) == vform(T["C"][0][i]); k += 1
-    assert el(k) == mont(T["C"][0][0]); k += 1
-    for i in range(t):
-        for j in range(t):
-            assert el(k) == mont(T["M"][i][j]); k += 1
-    for i in range(t):
-        for j in range(t):
-            assert el(k) == mont(T["PRE"][i][j]); k += 1
-    for i in range(t):
-        for j in range(t):
-            assert el(k) == mont(T["TAIL0"][i][j]); k += 1
+    pos = [0]
+
+    def expect(values, form=mont):
+        for x in values:
+            assert el(pos[0]) == form(x), pos[0]
+            pos[0] += 1
+
+    flat = lambda rows: [x for row in rows for x in row]
+    ident = lambda x: x
+    # ---- every schedule
+    expect([1], lambda _: R * R % P)
+    expect(T["C"][0], vform)
+    expect([T["C"][0][0]])
+    expect(flat(T["M"]))
+    expect(flat(T["TAIL0"]))
     for r in range(3):
-        for i in range(t):
-            assert el(k) == vform(T["C"][r + 1][i]); k += 1
-    assert el(k) == vform(T["k"][0]); k += 1
-    for i in range(1, t):
-        assert el(k) == 0; k += 1
+        expect(T["C"][r + 1], vform)
+    for r in range(3):
+        expect(T["C"][4 + rp + r + 1], vform)
+    expect(T["M"][0], ident)
+    expect(T["M"][0])
+    # round 0 on unconverted inputs: X0 = (C_0[0])^5 / R^4, R0_M = M R^6, IN_C = C_0
+    expect([pow(T["C"][0][0], 5, P) * pow(R, -4, P) % P], ident)
+    expect(flat(T["M"]), lambda x: x * pow(R, 6, P) % P)
+    expect(T["C"][0], ident)
+    # ---- history recurrence (widths 2..6)
+    if t <= 6:
+        H = opt_model.derive_hr(t, T)
+        expect(flat(H["pre"]))
+        expect(H["pre_v"], vform)
+        for j in range(1, n):
+            expect(reversed(H["boot"][j]))                   # newest z first
+        for al, be, const in H["steady"] + H["exit"]:
+            expect(al)
+            expect(be)
+            expect([const], vform)
+    # ---- paired sparse rounds
+    expect(flat(T["PRE"]))
+    expect([T["k"][0]], vform)
+    expect([0] * (t - 1), ident)
     n_pairs = rp // 2 if opt_model.paired(t) else 0
     for jp in range(n_pairs):
         (vA, wA, kA), (vB, wB, kB) = T["scaled"][2 * jp], T["scaled"][2 * jp + 1]
-        for i in range(t - 1):
-            assert el(k) == mont(vA[i]); k += 1
-        assert el(k) == vform(kA); k += 1
-        for i in range(t - 1):
-            assert el(k) == mont(vB[i]); k += 1
-        assert el(k) == mont(sum(a * b for a, b in zip(vB, wA)) % P); k += 1
-        assert el(k) == vform(kB); k += 1
-        for i in range(t - 1):
-            assert el(k) == mont(wA[i]); k += 1
-            assert el(k) == mont(wB[i]); k += 1
+        expect(vA)
+        expect([kA], vform)
+        expect(vB)
+        expect([sum(a * b for a, b in zip(vB, wA)) % P])
+        expect([kB], vform)
+        expect([x for pair in zip(wA, wB) for x in pair])
     for j in range(2 * n_pairs, rp):
         v, w, kk = T["scaled"][j]
-        for i in range(t - 1):
-            assert el(k) == mont(v[i]); k += 1
-        for i in range(t - 1):
-            assert el(k) == mont(w[i]); k += 1
-        assert el(k) == vform(kk); k += 1
-    for i in range(1, t):
-        assert el(k) == mont(T["D"][i]); k += 1
-    for r in range(3):
-        for i in range(t):
-            assert el(k) == vform(T["C"][4 + rp + r + 1][i]); k += 1
-    for j in range(t):
-        assert el(k) == T["M"][0][j]; k += 1
-    for j in range(t):
-        assert el(k) == mont(T["M"][0][j]); k += 1
-    for j in range(rp):
-        exp = 0 if j == 0 else sum(a * b for a, b in zip(T["scaled"][j][0], T["scaled"][j - 1][1])) % P
-        assert el(k) == mont(exp); k += 1
-    if t == 3:                                   # rows over Q = (a, u', z_a, z_b) (Layout<3>::FB)
-        F = opt_model.derive_fb2(t, T)
-        for row in F["pre"]:
-            for x in row:
-                assert el(k) == mont(x); k += 1
-        for x in F["pre_v"]:
-            assert el(k) == vform(x); k += 1
-        assert el(k) == mont(F["entry"][0][0]); k += 1
-        assert el(k) == mont(F["entry"][0][1]); k += 1
-        assert el(k) == vform(F["entry"][1]); k += 1
-        for ha, ka, hb, c, kb in F["pairs"]:
-            for x in ha:
-                assert el(k) == mont(x); k += 1
-            assert el(k) == vform(ka); k += 1
-            for x in hb:
-                assert el(k) == mont(x); k += 1
-            assert el(k) == mont(c); k += 1
-            assert el(k) == vform(kb); k += 1
-        for h, kk in F["exit"]:
-            for x in h:
-                assert el(k) == mont(x); k += 1
-            assert el(k) == vform(kk); k += 1
-    # round 0 on unconverted inputs: X0 = (C_0[0])^5 / R^4, R0_M = M R^6, IN_C = C_0
-    assert el(k) == pow(T["C"][0][0], 5, P) * pow(R, -4, P) % P; k += 1
-    for i in range(t):
-        for j in range(t):
-            assert el(k) == T["M"][i][j] * pow(R, 6, P) % P; k += 1
-    for i in range(t):
-        assert el(k) == T["C"][0][i]; k += 1
-    assert k * 8 == words
+        expect(v)
+        expect(w)
+        expect([kk], vform)
+    expect(T["D"][1:])
+    expect([0 if j == 0 else sum(a * b for a, b in zip(T["scaled"][j][0], T["scaled"][j - 1][1])) % P for j in range(rp)])
+    assert pos[0] * 8 == words
 
 
 def test_mont_sqr_equals_mul(emu):

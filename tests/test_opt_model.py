@@ -63,3 +63,16 @@ def test_rows_over_existing_values_schedule_equals_dense():
         ins = [rng.randrange(O.P) for _ in range(2)]
         tag = 0 if i % 3 else rng.randrange(O.P)
         assert opt_model.hash_opt_fb2(ins, tag, T, F) == O.poseidon_permute_hash(ins, tag)
+
+
+@pytest.mark.parametrize("t", list(range(2, 9)))
+def test_history_recurrence_schedule_equals_dense(t):
+    """The partial rounds as a recurrence over the last t-1 S-box inputs and outputs (Layout<T>::HR)."""
+    T = opt_model.derive(t)
+    H = opt_model.derive_hr(t, T)
+    assert len(H["steady"]) == T["rp"] - (t - 1) and len(H["exit"]) == t - 1
+    rng = random.Random(35 + t)
+    for i in range(6):
+        ins = [rng.randrange(O.P) for _ in range(t - 1)]
+        tag = 0 if i % 3 else rng.randrange(O.P)
+        assert opt_model.hash_opt_hr(ins, tag, T, H) == O.poseidon_permute_hash(ins, tag)
