@@ -304,73 +304,6 @@ std::vector<uint32_t> build_opt(void) {
             put_row(L::HR_EXIT + i * L::HR_STRIDE, rp, e, D[1 + i]);
         }
     }
-    if constexpr (L::FB) {
-        // width 3: rows over Q = (a, u', z_a, z_b) (Layout::FB; derive_fb2 in tests/opt_model.py)
-        static_assert(!L::FB || T == 3, "derived for width 3");
-        if (rp % 2 != 1) throw std::runtime_error("functional basis expects an odd round count");
-        auto dot2 = [](const F* x, const std::vector<F>& y) { return add(mul(x[0], y[0]), mul(x[1], y[1])); };
-        struct M2 { F m[2][2]; };
-        auto inv2 = [](const std::vector<F>& r0, const std::vector<F>& r1) {
-            const F det = sub(mul(r0[0], r1[1]), mul(r0[1], r1[0]));
-            if (det.is_zero()) throw std::runtime_error("dependent rows in the functional basis");
-            const F di = inv(det);
-            return M2{{{mul(r1[1], di), neg(mul(r0[1], di))}, {neg(mul(r1[0], di)), mul(r0[0], di)}}};
-        };
-        for (int x = 0; x < T; x++) {
-            put_mont(tbl, L::FB_PRE_M + x, PRE[x]);
-            put_mont(tbl, L::FB_PRE_M + T + x, add(mul(vs[1][0], PRE[T + x]), mul(vs[1][1], PRE[2 * T + x])));
-            put_mont(tbl, L::FB_PRE_M + 2 * T + x, add(mul(vs[2][0], PRE[T + x]), mul(vs[2][1], PRE[2 * T + x])));
-        }
-        put_v(tbl, L::FB_PRE_V + 0, k[0]);
-        put_v(tbl, L::FB_PRE_V + 1, ks[1]);
-        put_v(tbl, L::FB_PRE_V + 2, ks[2]);
-        {   // v_0 = al v_1 + be v_2
-            const M2 vi = inv2(vs[1], vs[2]);
-            const F al = add(mul(vs[0][0], vi.m[0][0]), mul(vs[0][1], vi.m[1][0]));
-            const F be = add(mul(vs[0][0], vi.m[0][1]), mul(vs[0][1], vi.m[1][1]));
-            put_mont(tbl, L::FB_ENTRY + 0, al);
-            put_mont(tbl, L::FB_ENTRY + 1, be);
-            put_v(tbl, L::FB_ENTRY + 2, sub(ks[0], add(mul(al, ks[1]), mul(be, ks[2]))));
-        }
-        // pair 0 reads Q = (F1, u_1, z_0, F2): a_0 = F1 + (v_1.w_0) z_0 ; b_0 = F2 + (v_2.w_0) z_0
-        F ha[4] = {one(), zero(), dot2(&vs[1][0], ws[0]), zero()}, ka = zero();
-        F hb[4] = {zero(), zero(), dot2(&vs[2][0], ws[0]), one()}, kb = zero();
-        const int n_pairs = rp / 2;
-        for (int p = 0; p < n_pairs; p++) {
-            const int a = 2 * p + 1, b = 2 * p + 2, base = L::FB_PART + p * L::FB_STRIDE;
-            const F c = dot2(&vs[b][0], ws[a]);
-            for (int x = 0; x < 4; x++) {
-                put_mont(tbl, base + L::FB_HA + x, ha[x]);
-                put_mont(tbl, base + L::FB_HB + x, hb[x]);
-            }
-            put_v(tbl, base + L::FB_KA, ka);
-            put_mont(tbl, base + L::FB_HB + 4, c);
-            put_v(tbl, base + L::FB_KB, kb);
-            const M2 vi = inv2(vs[a], vs[b]);
-            for (int r = 0; r < 2; r++) {
-                F f[2], cst;
-                if (p + 1 < n_pairs) {
-                    f[0] = vs[a + 2 + r][0], f[1] = vs[a + 2 + r][1], cst = ks[a + 2 + r];
-                } else {
-                    f[0] = r == 0 ? one() : zero(), f[1] = r == 0 ? zero() : one(), cst = D[1 + r];
-                }
-                const F g0 = add(mul(f[0], vi.m[0][0]), mul(f[1], vi.m[1][0]));
-                const F g1 = add(mul(f[0], vi.m[0][1]), mul(f[1], vi.m[1][1]));
-                F* h = r == 0 ? ha : hb;
-                h[0] = g0;
-                h[1] = g1;                                                    // b = u' - z_b - c z_a
-                h[2] = sub(dot2(f, ws[a]), mul(c, g1));
-                h[3] = sub(dot2(f, ws[b]), g1);
-                (r == 0 ? ka : kb) = sub(cst, add(mul(g0, ks[a]), mul(g1, ks[b])));
-            }
-        }
-        for (int x = 0; x < 4; x++) {
-            put_mont(tbl, L::FB_EXIT + L::FB_X_H1 + x, ha[x]);
-            put_mont(tbl, L::FB_EXIT + L::FB_X_H2 + x, hb[x]);
-        }
-        put_v(tbl, L::FB_EXIT + L::FB_X_K1, ka);
-        put_v(tbl, L::FB_EXIT + L::FB_X_K2, kb);
-    }
     {
         // round 0 on unconverted inputs (Layout::R0_M): M R^6, (C_0[0])^5 / R^4, C_0 canonical.
         // to_mont multiplies by R, from_mont divides by it.

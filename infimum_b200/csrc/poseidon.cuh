@@ -71,9 +71,8 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 // The scale comes off in the first round of the second half, whose matrix has
 // column 0 multiplied by lambda_RP^5 (TAIL0_M).
 //
-// Three forms of the partial section live in the table (all exact rewritings of the same map):
+// Two forms of the partial section live in the table (both exact rewritings of the same map):
 //   * the history recurrence (HR, widths 2..6; what the per-thread kernels run),
-//   * width 3's rows over Q (FB; built only without HR, -DINF_NO_HR),
 //   * the paired sparse rounds (widths 7, 8, and every width's warp-cooperative schedule, coop.cuh).
 
 // History recurrence (derive_hr in tests/opt_model.py).  The passive state s[1..] (n = T-1 elements) is
@@ -91,12 +90,6 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 INF_HD constexpr bool hr_rounds(int) { return false; }
 #else
 INF_HD constexpr bool hr_rounds(int t) { return t >= 2 && t <= 6; }
-#endif
-// Width 3's rows over Q (Layout::FB), kept as the alternative to HR.
-#ifdef INF_NO_FB
-INF_HD constexpr bool fb_rounds(int) { return false; }
-#else
-INF_HD constexpr bool fb_rounds(int t) { return t == 3 && !hr_rounds(t); }
 #endif
 #ifndef INF_HR_UNROLL
 #define INF_HR_UNROLL 1      // rounds per loop body: 1 shifts the history with register moves, n renames them away
@@ -138,27 +131,8 @@ struct Layout {
     static constexpr int HR_ROUNDS = RP - N;
     static constexpr int HR_EXIT = HR_PART + HR_ROUNDS * HR_STRIDE;   // n rows at j = RP: the plain s[1..] (+ D)
     static constexpr int HR_END = HR ? HR_EXIT + N * HR_STRIDE : COMMON_END;
-    // ---- width 3, rows over Q (derive_fb2 in tests/opt_model.py) ----------------------------------
-    // The two passive state elements are determined by the two functionals the NEXT pair of rounds
-    // reads, a = v'_A . s[1..] + k'_A and b = v'_B . s[1..] + k'_B, and a pair becomes
-    //     z_a = u^5 ; n = z_a + a ; z_b = n^5 ; u' = z_b + b + c z_a .
-    // b is only ever added, so it never has to exist as a reduced value: with b = u' - z_b - c z_a the
-    // next pair's rows are rows over Q = (a, u', z_a, z_b), four values that exist anyway,
-    //     a' = ha . Q + ka ;   b' + c' z_a' = (hb, c') . (Q, z_a') + kb       (once z_a' is known)
-    // 9 products and 2 reductions per pair beside the two S-boxes, instead of 9 and 4.  RP = 57 is odd:
-    // the odd round goes first, in the plain form.
-    static constexpr bool FB = fb_rounds(T);
-    static constexpr int FB_PRE_M = HR_END;              // [T][T] rows 1, 2 of PRE_M mapped to (F1, F2) = v'_{1,2} . s[1..]
-    static constexpr int FB_PRE_V = FB_PRE_M + T * T;    // [T]    (k_0, k'_1, k'_2)
-    static constexpr int FB_ENTRY = FB_PRE_V + T;        // al, be, k: u_1 = z_0 + al F1 + be F2 + k
-    static constexpr int FB_PART = FB_ENTRY + 3;         // RP/2 records: ha[4], ka, hb[4], c, kb
-    static constexpr int FB_STRIDE = 11;
-    static constexpr int FB_HA = 0, FB_KA = 4, FB_HB = 5, FB_KB = 10;
-    static constexpr int FB_EXIT = FB_PART + (RP / 2) * FB_STRIDE;   // h1[4], k1, h2[4], k2: the plain s[1], s[2] (+ D)
-    static constexpr int FB_X_H1 = 0, FB_X_K1 = 4, FB_X_H2 = 5, FB_X_K2 = 9, FB_X_COUNT = 10;
-    static constexpr int FB_END = FB ? FB_EXIT + FB_X_COUNT : HR_END;
     // ---- paired sparse rounds ----------------------------------------------------------------------
-    static constexpr int PRE_M = FB_END;                 // [T][T] MDS with the sparse prefix merged
+    static constexpr int PRE_M = HR_END;                 // [T][T] MDS with the sparse prefix merged
     static constexpr int PRE_V = PRE_M + T * T;          // [T]   (k_0, 0, ..., 0)
     static constexpr bool PAIRED = paired_rounds(T);
     // single round record [2T-1] : v'[T-1], w'[T-1], k'
@@ -178,7 +152,7 @@ struct Layout {
     static constexpr int WORDS = COUNT * 8;
     // what the per-thread kernels read (a unit that only has those, leaves.cu, keeps just this prefix
     // in its constant bank)
-    static constexpr int THREAD_COUNT = HR ? HR_END : FB ? FB_END : COUNT;
+    static constexpr int THREAD_COUNT = HR ? HR_END : COUNT;
     static constexpr int THREAD_WORDS = THREAD_COUNT * 8;
     // offsets inside a pair record
     static constexpr int P_VA = 0, P_KA = T - 1, P_VB = T, P_CB = 2 * T - 1, P_KB = 2 * T, P_W = 2 * T + 1;
@@ -262,8 +236,8 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
     // ---- first half: rounds 0..3 (round 3 uses the merged matrix) ----------
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-        constexpr int PM = L::HR ? L::HR_PRE_M : L::FB ? L::FB_PRE_M : L::PRE_M;
-        constexpr int PV = L::HR ? L::HR_PRE_V : L::FB ? L::FB_PRE_V : L::PRE_V;
+        constexpr int PM = L::HR ? L::HR_PRE_M : L::PRE_M;
+        constexpr int PV = L::HR ? L::HR_PRE_V : L::PRE_V;
         const uint32_t* m = tbl + (r == 0 && raw_in ? L::R0_M : r < 3 ? L::FULL_M : PM) * 8;
         const uint32_t* v = tbl + (r < 3 ? L::FULL_V + r * T : PV) * 8;
         INF_LOCKSTEP_SYNC();
@@ -313,47 +287,6 @@ INF_HD void poseidon_rounds(uint32_t (&out)[8], uint32_t (&s)[T][8], const uint3
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) s[0][k] = h[0][k];
-    } else if constexpr (L::FB) {
-        // ---- partial rounds, width 3 (Layout::FB): round 3 left s = (u_0, F1, F2) ---------------
-        // q = (a, u, z_a of the previous pair, z_b of the previous pair, z_a), contiguous for the
-        // four- and five-term rows.  Ranges: a, u, F < 2p + eps (range steps), z < 1.7 p; the five-term
-        // row is below (0.189 * 9.4 + 1) p = 2.8 p before its range step; the sums z + row are below
-        // 3.7 p before theirs.
-        static_assert(!L::FB || (T == 3 && L::RP % 2 == 1), "derived for width 3 (odd round count)");
-        uint32_t q[5][8];
-        {
-            const uint32_t* pt = tbl + L::FB_ENTRY * 8;
-            uint32_t a[8];
-            sbox(q[2], s[0]);                                                   // z_0
-            dot<2, 8, true>(a, &s[1][0], pt, pt + 2 * 8);
-            add8(q[1], q[2], a);                                                // u_1
-            csub2p(q[1]);
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[0][k] = s[1][k], q[3][k] = s[2][k];
-        }
-#pragma unroll 1
-        for (int j = 0; j < L::RP / 2; j++) {
-            const uint32_t* pt = tbl + (L::FB_PART + j * L::FB_STRIDE) * 8;
-            uint32_t n[8], na[8], tt[8];
-            INF_LOCKSTEP_SYNC();
-            sbox(q[4], q[1]);                                                   // z_a = u^5
-            dot<4, 8, true>(na, &q[0][0], pt + L::FB_HA * 8, pt + L::FB_KA * 8);    // a
-            dot<5, 8, true>(tt, &q[0][0], pt + L::FB_HB * 8, pt + L::FB_KB * 8);    // b + c z_a
-            add8(n, q[4], na);
-            csub2p(n);
-            sbox(q[3], n);                                                      // z_b = n^5
-            add8(q[1], q[3], tt);                                               // u'
-            csub2p(q[1]);
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[0][k] = na[k], q[2][k] = q[4][k];
-        }
-        {
-            const uint32_t* pt = tbl + L::FB_EXIT * 8;
-            dot<4, 8, true>(s[1], &q[0][0], pt + L::FB_X_H1 * 8, pt + L::FB_X_K1 * 8);
-            dot<4, 8, true>(s[2], &q[0][0], pt + L::FB_X_H2 * 8, pt + L::FB_X_K2 * 8);
-#pragma unroll
-            for (int k = 0; k < 8; k++) s[0][k] = q[1][k];
-        }
     } else {
     // ---- partial rounds -----------------------------------------------------
     // q[0..T-2] = s[1..T-1], q[T-1] = z_a, q[T] = z_b: contiguous, so that the lazy

@@ -30,6 +30,14 @@ def sbox(x, track):
     return x5
 
 
+def csub4p(x):
+    return max(4 + EPS, x - 4)
+
+
+def hr_rounds(t):
+    return 2 <= t <= 6                                       # poseidon.cuh: hr_rounds
+
+
 def run(t, rp):
     worst = [0.0]
     rs = csub2p if t > 2 else (lambda x: x)                  # poseidon.cuh: RS = T > 2
@@ -39,10 +47,28 @@ def run(t, rp):
         assert x < LIM, (t, x)
         return x
 
-    s = [track(dot([(LIM, 1.0)]))] * t                     # absorb: raw 256-bit x R^2 + V
+    # absorb_raw: any 256-bit integer, two range steps, + C_0 (< p), one more
+    s = [csub2p(track(csub2p(csub4p(LIM)) + 1.0))] * t
     for r in range(4):                                       # first half
         x = [sbox(v, track) for v in s]
         s = [rs(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
+    if hr_rounds(t):
+        # history recurrence: rows over the last n S-box inputs (u) and outputs (z)
+        n = t - 1
+        hr_range = (lambda x: csub2p(csub4p(x))) if n >= 5 else csub2p      # poseidon.cuh: hr_range
+        us, zs = [s[0]], []
+        for j in range(n):                                   # bootstrap rounds: F_j + rows over the z so far
+            zs.append(sbox(us[-1], track))
+            v = s[1 + j] if j == 0 else csub2p(track(track(dot([(z, 1.0) for z in zs[:j]], 0)) + s[1 + j]))
+            us.append(csub2p(track(zs[-1] + v)))
+        for j in range(n, rp):
+            z = sbox(us[-1], track)
+            v = hr_range(track(dot([(u, 1.0) for u in us[-n:]] + [(x, 1.0) for x in zs[-n:]])))
+            zs.append(z)
+            us.append(csub2p(track(z + v)))
+        rest = [hr_range(track(dot([(u, 1.0) for u in us[-n:]] + [(x, 1.0) for x in zs[-n:]]))) for _ in range(n)]
+        s = [us[-1]] + rest
+        rp = 0                                               # nothing left for the paired form below
     ri = csub2p if t >= 5 else (lambda x: x)                 # poseidon.cuh: RI = T >= 5
     for j in range(rp // 2):                                 # paired partial rounds, unit leading coefficient
         za = sbox(s[0], track)
@@ -54,7 +80,8 @@ def run(t, rp):
         z = sbox(s[0], track)
         n0 = csub2p(track(ri(track(dot([(si, 1.0) for si in s[1:]]))) + z))
         s = [n0] + [csub2p(track(si + track(dot([(z, 1.0)], 0)))) for si in s[1:]]
-    s = [s[0]] + [csub2p(track(si + 1.0)) for si in s[1:]]
+    if not hr_rounds(t):
+        s = [s[0]] + [csub2p(track(si + 1.0)) for si in s[1:]]
     for r in range(3):
         x = [sbox(v, track) for v in s]
         s = [rs(track(dot([(xi, 1.0) for xi in x]))) for _ in range(t)]
