@@ -10,6 +10,12 @@
 //   * partial rounds in sparse form: the constants of the partial section are
 //     pushed forward until only a scalar on s[0] remains, and the dense MDS is
 //     factored so that a partial round costs 2t-1 products instead of t^2;
+//   * widths 2..6: that sparse form turned into a recurrence over the S-box
+//     inputs and outputs of the last t-1 rounds (Layout::HR below) -- 2(t-1)
+//     products and ONE reduction per round, no passive state to update;
+//   * round 0 on the inputs as they arrive (no Montgomery conversion: its
+//     matrix carries the scale) and, under domain tag 0, with the S-box of the
+//     constant state[0] read from the table;
 //   * in the last round only row 0 of the MDS is evaluated (the reference
 //     discards the rest, poseidon.rs:205), against the non-Montgomery copy of
 //     that row, so the dot product lands directly on the canonical value.
@@ -38,8 +44,8 @@ INF_HD constexpr int partial_rounds(int t) {
          : t == 8 ? 64 : t == 9 ? 63 : t == 10 ? 60 : t == 11 ? 66 : t == 12 ? 60 : 65;
 }
 
-// Paired partial rounds (widths >= 4 with an even number of partial rounds):
-// two partial rounds share the update of s[1..]:
+// Paired partial rounds (the per-thread kernels of widths 7 and 8, and the table every
+// width's warp-cooperative schedule reads): two partial rounds share the update of s[1..]:
 //     round A:  z_a = u^5 ;  n = z_a + v'_A . s[1..] + k'_A
 //     round B:  z_b = n^5 ;  u = z_b + v'_B . s[1..] + c_B * z_a + k'_B ,   c_B = v'_B . w'_A
 //     then      s_i += w'_A[i] * z_a + w'_B[i] * z_b        (one 2-term lazy dot, ONE reduction)
