@@ -418,16 +418,17 @@ static int level_pad(unsigned grid) {
     return grid <= 4 * n ? 55 * 1024 : 44 * 1024;
 }
 
-// Levels with at most this many parents go to the warp-cooperative kernel: the measured
-// crossover with the per-thread kernel is 16 384 parents for hash2 (203 vs 196 us) and
-// between 8 192 and 16 384 for hash5 (profiles/r02_tree_levels.md, tools/level_probe.py).
-// INF_COOP_MAX overrides, 0 disables.
+// Levels with at most this many parents go to the warp-cooperative kernel.  Measured crossover
+// with the per-thread kernel (profiles/r02_tree_levels.md, tools/level_probe.py): for hash2 the
+// cooperative kernel takes 116 / 172 / 203 us at 8 192 / 12 288 / 16 384 parents against 178 us for
+// one thread's hash (196 us before the history recurrence, when the threshold was 16 384); for
+// hash5 218 us at 8 192 and ~320 at 12 288 against 338.  INF_COOP_MAX overrides, 0 disables.
 static uint64_t coop_max() {
     static long long v = -1;
     static bool set_on[64] = {};
     if (v < 0) {
         const char* e = getenv("INF_COOP_MAX");
-        v = e ? atoll(e) : (T >= 5 ? 8192 : 16384);
+        v = e ? atoll(e) : (T >= 5 ? 8192 : 12288);
     }
     int dev = 0;
     cudaGetDevice(&dev);

@@ -228,7 +228,7 @@ def test_optimised_kernel_equals_dense_kernel_on_device(ib, n_inputs):
 
 @pytest.mark.parametrize("n_inputs", range(1, 8))
 def test_small_and_large_batches_take_different_kernels_same_results(ib, n_inputs):
-    """Batches of at most 16 384 (widths <= 4) / 8 192 hashes run the warp-cooperative kernel (one
+    """Batches of at most 12 288 (widths <= 4) / 8 192 hashes run the warp-cooperative kernel (one
     hash spread over width + 1 warps), larger ones one hash per thread: both against the oracle, at the
     sizes where the cooperative kernel changes shape (one lane, a ragged warp, more than one block per
     SM = rotated role layout, its largest batch), with a domain tag and in either wire order."""
@@ -238,7 +238,7 @@ def test_small_and_large_batches_take_different_kernels_same_results(ib, n_input
     h = ib.Poseidon.new_circom(n_inputs)
     assert (h.hash_batch(raw) == exp).all()
     row = n_inputs * 32
-    for m in (1, 31, 33, 4736 + 5, 8192, 8193, 16384):
+    for m in (1, 31, 33, 4736 + 5, 8192, 8193, 12288, 12289, 16384):
         assert (h.hash_batch(raw[: m * row]) == exp[:m]).all(), m
     tag = 0x1234567890abcdef << 100
     ht = ib.Poseidon.with_domain_tag_circom(n_inputs, tag)
