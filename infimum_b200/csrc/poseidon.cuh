@@ -91,7 +91,7 @@ INF_HD constexpr bool paired_rounds(int t) { return t >= 2; }
 // hash5, -11 % per hash2).  The first n rounds read their rows F_j = v'_j . s[1..]^(0) + k'_j straight
 // out of the merged round-3 matrix plus the few z that exist by then; after the last round n rows over
 // the same history return the plain s[1..] (constants D folded in).  The widest row sums 2n terms:
-// bounded by (0.189 (2n + 1.7n) + 1) p = 4.5 p < 2^256 for n = 5; widths 7 and 8 would overflow.
+// bounded by (0.189 (2n + 1.7n) + 1) p = 4.5 p < 2^256 = 5.29 p for n = 5; 5.2 p for n = 6 (no margin), 5.9 p for n = 7.
 #ifdef INF_NO_HR
 INF_HD constexpr bool hr_rounds(int) { return false; }
 #else
