@@ -166,7 +166,7 @@ void hostemu_redc(const uint32_t* x, uint32_t* r) {
     mont_redc(t, x);
     memcpy(r, t, 32);
 }
-// n-term lazy dot, n in 1..8: a = n x 8 limbs, b = n x 8 limbs, v = 8 limbs or NULL
+// n-term lazy dot, n in 1..10: a = n x 8 limbs, b = n x 8 limbs, v = 8 limbs or NULL
 int hostemu_dot(int n, const uint32_t* a, const uint32_t* b, const uint32_t* v, uint32_t* r) {
     uint32_t t[8];
     switch (n) {
@@ -178,6 +178,8 @@ int hostemu_dot(int n, const uint32_t* a, const uint32_t* b, const uint32_t* v, 
         case 6: dot<6, 8>(t, a, b, v); break;
         case 7: dot<7, 8>(t, a, b, v); break;
         case 8: dot<8, 8>(t, a, b, v); break;
+        case 9: dot<9, 8>(t, a, b, v); break;
+        case 10: dot<10, 8>(t, a, b, v); break;     // the widest row of the history recurrence (t = 6)
         default: return -1;
     }
     memcpy(r, t, 32);
@@ -187,6 +189,19 @@ void hostemu_csub2p(uint32_t* x) {
     uint32_t t[8];
     memcpy(t, x, 32);
     csub2p(t);
+    memcpy(x, t, 32);
+}
+void hostemu_csub4p(uint32_t* x) {
+    uint32_t t[8];
+    memcpy(t, x, 32);
+    csub4p(t);
+    memcpy(x, t, 32);
+}
+// Range steps of a history-recurrence row of n passive elements (hr_range<N>, poseidon.cuh).
+void hostemu_hr_range(int n, uint32_t* x) {
+    uint32_t t[8];
+    memcpy(t, x, 32);
+    if (n >= 5) hr_range<5>(t); else hr_range<1>(t);
     memcpy(x, t, 32);
 }
 void hostemu_csub_p_exact(uint32_t* x) {

@@ -88,6 +88,40 @@ def test_redc_and_range_steps(emu):
             assert val(z) == (x - P if x >= P else x)
 
 
+def test_range_step_of_4p_and_the_widest_recurrence_row(emu):
+    """csub4p (absorb_raw, hr_range for five passive elements) and the ten-term row of the width-6 recurrence at
+    the top of its range: five S-box inputs just under 2p + 2^224, five S-box outputs at 1.7 p, every constant
+    p - 1, the additive constant p - 1 -- the tightest accumulator of the whole schedule (tools/bounds.py: 4.59 p
+    of 5.29 p).  No overflow, exact value mod p, below 2p + 2^224 after its range steps."""
+    rng = random.Random(6)
+    for x in EDGE_VALUES + [rng.randrange(R) for _ in range(300)] + [4 * P - 1, 4 * P, 4 * P + (1 << 224), 4 * P + (1 << 225)]:
+        y = limbs(x)
+        emu.hostemu_csub4p(y)
+        assert val(y) % P == x % P
+        assert val(y) < max(4 * P + (1 << 224), x - 4 * P + 1)
+        emu.hostemu_csub2p(y)
+        assert val(y) < 2 * P + (1 << 224)                  # any 256-bit integer: what absorb_raw relies on
+    base = emu.hostemu_overflow_count()
+    U80 = ctypes.c_uint32 * 80
+    pack = lambda xs: U80(*[(x >> (32 * i)) & 0xFFFFFFFF for x in xs for i in range(8)])
+    hi_u, hi_z = 2 * P + (1 << 224) - 1, 17 * P // 10
+    cases = [([hi_u] * 5 + [hi_z] * 5, [P - 1] * 10, P - 1)]
+    for _ in range(40):
+        cases.append(([rng.randrange(2 * P + (1 << 224)) for _ in range(5)] + [rng.randrange(hi_z) for _ in range(5)],
+                      [rng.randrange(P) for _ in range(10)], rng.randrange(P)))
+    for a, b, v in cases:
+        r = U8()
+        # V enters the accumulator as is and is divided by R with everything else
+        assert emu.hostemu_dot(10, pack(a), pack(b), limbs(v), r) == 0
+        exp = (sum(x * y for x, y in zip(a, b)) + v) * RINV % P
+        got = val(r)
+        assert got % P == exp
+        assert got < max(2 * P + (1 << 224), int(4.6 * P) - 2 * P)      # dot applies one step of 2p itself
+        emu.hostemu_hr_range(5, r)
+        assert val(r) % P == exp and val(r) < 2 * P + (1 << 224)
+    assert emu.hostemu_overflow_count() == base
+
+
 @pytest.mark.parametrize("t", range(2, 9))
 def test_optimised_hash_equals_oracle(emu, t):
     rng = random.Random(200 + t)
